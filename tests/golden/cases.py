@@ -1,0 +1,67 @@
+"""Seeded inputs shared by make_golden.py (runs the reference source on the TF1 shim, in the build
+container only) and by the tests that compare the oracle / CUDA path with the committed fixtures."""
+import numpy as np
+
+from kfnet_b200 import synth
+
+SMALL_HW = (64, 96)          # image size of the small cases -> 8x12 label grid
+WEIGHT_SEED = 0
+
+
+def weights():
+    return synth.make_weights(WEIGHT_SEED)
+
+
+def small_images(n, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, size=(SMALL_HW[0] + 16, SMALL_HW[1] + 16, 3)).astype(np.float32)
+    # blur a little so neighbouring frames correlate, then shift per frame
+    k = np.ones((3, 3), np.float32) / 9.0
+    sm = np.zeros_like(base)
+    for dy in range(3):
+        for dx in range(3):
+            sm += k[dy, dx] * np.roll(np.roll(base, dy - 1, 0), dx - 1, 1)
+    out = np.empty((n,) + SMALL_HW + (3,), np.float32)
+    for i in range(n):
+        oy, ox = int(rng.integers(0, 16)), int(rng.integers(0, 16))
+        out[i] = np.floor(sm[oy:oy + SMALL_HW[0], ox:ox + SMALL_HW[1]])
+    return out
+
+
+def small_state(seed):
+    rng = np.random.default_rng(seed)
+    h, w = SMALL_HW[0] // 8, SMALL_HW[1] // 8
+    coord = rng.normal(size=(1, h, w, 3))
+    unc = rng.uniform(0.02, 0.3, size=(1, h, w, 1))
+    return coord, unc
+
+
+def bilinear_case():
+    """imgs [2,5,7,3]; coords cover interior, exact integers, x=W-1, x in [W-1,W), negatives, far OOB."""
+    rng = np.random.default_rng(11)
+    imgs = rng.normal(size=(2, 5, 7, 3))
+    xs = np.array([0.0, 0.25, 3.5, 5.0, 5.75, 6.0, 6.3, 6.999, 7.0, 9.5, -0.5, -1.0, -2.5, 2.0])
+    ys = np.array([0.0, 1.5, 3.0, 3.9, 4.0, 4.2, 5.0, -0.3, -1.7, 2.0])
+    gx, gy = np.meshgrid(xs, ys)
+    coords = np.stack([gx, gy], -1)[None].repeat(2, 0)          # [2,10,14,2]
+    return imgs, coords
+
+
+def volume_case():
+    rng = np.random.default_rng(12)
+    f1 = rng.normal(size=(1, 9, 11, 4))
+    f2 = rng.normal(size=(1, 9, 11, 4))
+    return f1, f2
+
+
+def full_images():
+    return synth.make_sequence(2, seed=1).astype(np.float32)
+
+
+def full_state():
+    rng = np.random.default_rng(21)
+    return rng.normal(size=(1, 60, 80, 3)), rng.uniform(0.02, 0.3, size=(1, 60, 80, 1))
+
+
+def transform():
+    return np.linalg.inv(synth.make_transform(2)).astype(np.float64)

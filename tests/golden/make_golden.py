@@ -1,0 +1,86 @@
+"""Generate tests/golden/*.npz by EXECUTING the reference's own model files on oracle/tf1_shim.
+
+Run in the build container only (needs /root/reference):  python -m tests.golden.make_golden
+The GPU box never runs this; tests read the committed .npz files.
+"""
+import builtins
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("KFNET_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+from tests.golden import cases  # noqa: E402
+
+# reference on the shim: shim first, then the reference root (cnn_wrapper, tools) and KFNet/ (util, KFNet)
+sys.path.insert(0, os.path.join(REF, "KFNet"))
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "tf1_shim"))
+builtins.basestring = str           # cnn_wrapper/network.py:84 is python-2 code
+
+import tensorflow as tf  # noqa: E402  (the shim)
+import KFNet as ref_kfnet  # noqa: E402  (/root/reference/KFNet/KFNet.py)
+from tools.util import bilinear_sampler as ref_bilinear  # noqa: E402
+import util as ref_util  # noqa: E402  (/root/reference/KFNet/util.py)
+
+assert ref_kfnet.__file__.startswith(REF), ref_kfnet.__file__
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def run_recursive(images, state, out, prefix):
+    spec = ref_kfnet.KFNetDataSpec(batch_size=2, image_size=images.shape[1:3])
+    net = ref_kfnet.KFNet(tf.constant(images), spec, train_scoordnet=False, train_oflownet=False)
+    last_coord, last_unc = (tf.constant(s) for s in state)
+    mc, mu = net.GetMeasureCoord2()
+    tc, tu, kc, ku = net.GetKFCoordRecursive(last_coord, last_unc)
+    nis = net.GetNIS(mc, mu, tc, tu)
+    T = tf.constant(cases.transform())
+    out.update({prefix + "feat": npy(net.temp_feat_maps), prefix + "measure_coord": npy(mc),
+                prefix + "measure_unc": npy(mu), prefix + "temp_coord": npy(tc), prefix + "temp_unc": npy(tu),
+                prefix + "kf_coord": npy(kc), prefix + "kf_unc": npy(ku), prefix + "nis": npy(nis),
+                prefix + "trans_kf_coord": npy(ref_util.ApplyTransform(kc, T))})
+    return net
+
+
+def main():
+    tf.set_dtype(torch.float64)
+    tf.set_variables(cases.weights())
+    out = {}
+
+    # 1. one recursive filter step at the small size (KFNet.GetKFCoordRecursive, KFNet.py:85-100)
+    run_recursive(cases.small_images(2, seed=5), cases.small_state(6), out, "small_rec_")
+
+    # 2. 4-frame unrolled filter (KFNet.GetKFCoordBatch, KFNet.py:102-146)
+    imgs4 = cases.small_images(4, seed=7)
+    spec = ref_kfnet.KFNetDataSpec(batch_size=4, image_size=imgs4.shape[1:3])
+    net = ref_kfnet.KFNet(tf.constant(imgs4), spec, False, False)
+    tc, tu, kc, ku = net.GetKFCoordBatch()
+    out.update(small_b4_temp_coord=npy(tc), small_b4_temp_unc=npy(tu), small_b4_kf_coord=npy(kc),
+               small_b4_kf_unc=npy(ku))
+
+    # 3. difference volume + offsets table (KFNet.BuildCoordVolume, KFNet.py:343-359)
+    f1, f2 = cases.volume_case()
+    diff, offs = net.BuildCoordVolume(tf.constant(f1), tf.constant(f2), 8)
+    out.update(volume_diff=npy(diff), volume_offsets=npy(offs))
+
+    # 4. bilinear sampler incl. edge behaviour (tools/util.py:3-94)
+    imgs, coords = cases.bilinear_case()
+    out["bilinear_out"] = npy(ref_bilinear(tf.constant(imgs), tf.constant(coords)))
+
+    # 5. full 480x640 recursive step on the synthetic sequence (frames 0,1)
+    run_recursive(cases.full_images(), cases.full_state(), out, "full_rec_")
+
+    path = os.path.join(HERE, "kfnet_reference_on_shim.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
