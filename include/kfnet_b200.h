@@ -1,0 +1,161 @@
+/* kfnet_b200 -- C ABI of the B200-native KFNet hot path (libkfnet_b200.so).
+ *
+ * The reference (zlthinker/KFNet, TF1/Python) has no FFI of its own: its "operator interface" for
+ * this path is the Python call surface of KFNet/KFNet.py + KFNet/eval.py.  Each entry point below
+ * names the reference function(s) it replaces (paths relative to the reference root); the Python
+ * host layer (kfnet_b200/) binds them with ctypes and mirrors the reference's names on top.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / C++ types.  Every call returns 0 on success or
+ *    a negative kfn_status; kfn_last_error() gives the thread-local message.  Nothing throws.
+ *  - All tensors are dense NHWC.  Device pointers are caller-owned (torch-allocated); the library
+ *    owns only the opaque handle (packed weights, TMA descriptors, scratch it allocates at finalize).
+ *  - Calls enqueue work on `stream` (a cudaStream_t passed as void*) and return; no host sync,
+ *    except the *_host entry point which takes HOST buffers and synchronises before returning.
+ *  - One handle per device / rank; a handle is not thread-safe.
+ *  - There is NO CPU fallback: without a CUDA device kfn_create fails with KFN_ERR_CUDA.
+ */
+#ifndef KFNET_B200_H_
+#define KFNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define KFN_API __attribute__((visibility("default")))
+#else
+#define KFN_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kfn_handle kfn_handle;
+
+enum kfn_status {
+  KFN_OK = 0,
+  KFN_ERR_ARG = -1,       /* bad argument / shape / missing weight */
+  KFN_ERR_CUDA = -2,      /* CUDA runtime or driver error (message has the cudaError string) */
+  KFN_ERR_STATE = -3,     /* call order (e.g. forward before kfn_finalize_weights) */
+  KFN_ERR_WORKSPACE = -4  /* workspace too small */
+};
+
+/* Compute modes.
+ *  KFN_MODE_FP32 : fp32 CUDA-core implicit-GEMM convolutions, fp32 activations.  Numerics contract of the
+ *                  reference (all reference arithmetic is fp32); used for the 1e-4 parity configs.
+ *  KFN_MODE_BF16 : tcgen05.mma (kind::f16, bf16 operands, fp32 TMEM accumulators) fed by TMA; bf16
+ *                  activations between layers; fp32 for everything after the conv stacks.  The
+ *                  "bf16 compute / fp32 accumulate" configuration of BASELINE.json configs[3..4].      */
+enum kfn_mode { KFN_MODE_FP32 = 0, KFN_MODE_BF16 = 1 };
+
+/* geometry of the path (KFNet/KFNet.py:7-16,70; eval.py:49-50) */
+#define KFN_IMG_H 480
+#define KFN_IMG_W 640
+#define KFN_GRID_H 60
+#define KFN_GRID_W 80
+#define KFN_WINDOW 8      /* KFNet.py:369  64 // flow_sample_rate */
+#define KFN_FEAT_C 32
+
+KFN_API const char* kfn_version(void);
+KFN_API const char* kfn_last_error(void);
+
+/* image_h / image_w must be multiples of 64 (reference: 480x640, KFNetDataSpec.image_size KFNet.py:9). */
+KFN_API int kfn_create(kfn_handle** out, int device, int mode, int image_h, int image_w);
+KFN_API int kfn_destroy(kfn_handle* h);
+
+/* Weights by TF variable name and TF layout (restore scopes eval.py:66-68):
+ *   "<scope>/<layer>/kernel"  conv [kh,kw,Cin,Cout] | conv2d_transpose [kh,kw,Cout,Cin] | dense [in,out]
+ *   "<scope>/<layer>/bias"    [Cout]
+ * `data` is HOST fp32; dims/ndim must match the architecture.  Replaces RestoreFromScope (train.py:317-321). */
+KFN_API int kfn_load_weight(kfn_handle* h, const char* name, const float* data, const int64_t* dims, int ndim);
+/* Packs/uploads all weights for the handle's mode.  Fails if any variable is missing. */
+KFN_API int kfn_finalize_weights(kfn_handle* h);
+
+/* Bytes of caller-owned device workspace needed by the forward calls for up to `frames` frames per
+ * kfn_scoordnet_forward / kfn_oflow_feat_forward call and `pairs` frame pairs per kfn_oflownet_forward call. */
+KFN_API int64_t kfn_workspace_bytes(kfn_handle* h, int frames, int pairs);
+
+/* SCoordNet (cnn_wrapper/SCoordNet.py:18-44, preprocess :34-37; KFNet.GetMeasureCoord KFNet.py:82-83).
+ *   images : device uint8 [B,H,W,3]   (decode_png output, train.py:215-216, before the cast to float)
+ *   measure: device fp32  [B,H/8,W/8,4] = (coord xyz, sigma_z = exp(prediction ch3))                          */
+KFN_API int kfn_scoordnet_forward(kfn_handle* h, const uint8_t* images, int B, float* measure,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* OFlowNet feature tower + l2_normalize (KFNet.BuildOFlowFeat, KFNet.py:315-341).
+ *   feat: device fp32 [B,H/8,W/8,32]                                                                        */
+KFN_API int kfn_oflow_feat_forward(kfn_handle* h, const uint8_t* images, int B, float* feat,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Feature-difference ("cost") volume (KFNet.BuildCoordVolume, KFNet.py:343-359 + reshape :372).
+ *   diff[n, p, i, j, c] = f_cur[n,p,c] - f_prev[n, p + (j-4, i-4), c]   (0 where the shifted pixel is outside)
+ *   f_prev, f_cur: device fp32 [NP,GH,GW,32]; diff: device [NP*GH*GW, 8, 8, 32], fp32 if out_bf16==0 else bf16 */
+KFN_API int kfn_diff_volume(const float* f_prev, const float* f_cur, int NP, int GH, int GW, void* diff, int out_bf16,
+                    void* stream);
+
+/* OFlowNet on NP frame pairs (cnn_wrapper/OFlowNet.py:17-56 + KFNet.BuildOFlowNet KFNet.py:369-386):
+ * diff volume -> U-Net -> softmax -> soft-argmax flow; conv3b -> fc1 -> fc2 -> uncertainty -> exp*1e-2.
+ *   f_prev, f_cur : device fp32 [NP,GH,GW,32]
+ *   flow          : device fp32 [NP,GH,GW,2]  (flow_x, flow_y) = prob . offsets
+ *   sigma_w       : device fp32 [NP,GH,GW]    transition (process-noise) uncertainty
+ *   logits        : optional device fp32 [NP*GH*GW, 64] (NULL to skip)  pre-softmax U-Net output, k = i*8+j
+ *   argmax        : optional device int32 [NP,GH,GW]    argmax_k prob (diagnostic)                  */
+KFN_API int kfn_oflownet_forward(kfn_handle* h, const float* f_prev, const float* f_cur, int NP, float* flow,
+                         float* sigma_w, float* logits, int32_t* argmax, void* workspace,
+                         int64_t workspace_bytes, void* stream);
+
+/* Flow-guided bilinear warp + process noise + Kalman update + NIS + rigid transform, as a serial scan
+ * over T frames of S independent sequences (one CTA per sequence, filter state resident in shared memory).
+ * Replaces KFNet.BuildOFlowNet tail (KFNet.py:386-401), tools/util.py:bilinear_sampler, KFNet.BuildKFCoord
+ * (:148-162), KFNet.GetNIS (:174-184), KFNet/util.py:ApplyTransform and the state feedback / re-init of the
+ * eval.py loop (:87-104, :121-126).
+ *   measure  : fp32 [S,T,GH,GW,4] (xyz, sigma_z)           flow: fp32 [S,T,GH,GW,2]    sigma_w: fp32 [S,T,GH,GW]
+ *              (flow/sigma_w entry t belongs to the pair (t-1, t); entries with (first_index+t) % reinit_period == 0 are ignored)
+ *   state_in : fp32 [S,GH,GW,4] (last_coord, last_uncertainty; eval.py:49-50) or NULL when the scan starts on a re-init frame
+ *   state_out: fp32 [S,GH,GW,4] or NULL
+ *   transform: HOST fp32 [16] row-major 4x4, ALREADY inverted (train.py:51-52)
+ *   reinit_period: frames with (first_index + t) % reinit_period == 0 take the measurement as state and output
+ *                  (eval.py:94-101; reference value 500); <= 0 disables re-init (needs state_in)
+ *   nis_gate : eval.py:87-92 (--NIS): pixels with sum_c NIS > 7.815 take the transformed measurement in out_map only
+ *   out_map  : fp32 [S,T,GH,GW,4] = (T * kf_coord, 1 / kf_uncertainty)  -- the array eval.py:123 saves
+ *   temp, kf : optional fp32 [S,T,GH,GW,4] (temp_coord, temp_uncertainty) / (KF_coord, KF_uncertainty), untransformed
+ *   nis      : optional fp32 [S,T,GH,GW,3]
+ *   taps     : optional int32 [S,T,GH,GW,2] (floor(x+flow_x), floor(y+flow_y)) of the sampler (tools/util.py:36-39) */
+KFN_API int kfn_kalman_scan(const float* measure, const float* flow, const float* sigma_w, const float* state_in,
+                    float* state_out, const float* transform, int S, int T, int GH, int GW, int first_index,
+                    int reinit_period, int nis_gate, float* out_map, float* temp, float* kf, float* nis,
+                    int32_t* taps, void* stream);
+
+/* One recursive filter step for one frame (KFNet.GetKFCoordRecursive, KFNet.py:85-100): kfn_kalman_scan with
+ * S = T = 1, no re-init.  last/measure/temp/kf: fp32 [GH,GW,4]; flow [GH,GW,2]; sigma_w [GH,GW]. */
+KFN_API int kfn_flow_warp_kalman(const float* flow, const float* sigma_w, const float* last, const float* measure,
+                         const float* transform, int GH, int GW, float* temp, float* kf, float* nis,
+                         float* out_map, int32_t* taps, void* stream);
+
+/* Whole eval path for S sequences of T frames resident on the device (the batched, time-decoupled form of the
+ * eval.py loop: all conv work frame-parallel, then the scan).  images: device uint8 [S,T,H,W,3];
+ * out_map: device fp32 [S,T,GH,GW,4].  frames_per_batch / pairs_per_batch bound the workspace (see
+ * kfn_workspace_bytes) -- the extra per-sequence buffers (measure, feat, flow, sigma_w) come out of the
+ * same workspace: add kfn_sequence_extra_bytes(S,T). */
+KFN_API int64_t kfn_sequence_extra_bytes(kfn_handle* h, int S, int T);
+KFN_API int kfn_eval_sequences(kfn_handle* h, const uint8_t* images, int S, int T, const float* transform,
+                       int reinit_period, int nis_gate, int frames_per_batch, int pairs_per_batch,
+                       float* out_map, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* One packed layer of the path by name (per-layer parity tests and per-layer roofline measurements).
+ *   op_key: "<scope>/<layer>" for conv / dense layers, "<scope>/<layer>#p<k>" (k = 2*py+px) for one sub-pixel phase
+ *           of a conv2d_transpose (cnn_wrapper/network.py:116-135, :418-437).
+ *   in    : device NHWC [N,IH,IW,in_cs] -- fp32 in KFN_MODE_FP32, bf16 in KFN_MODE_BF16 (the first Cin channels are read;
+ *           for the Cin=3 first layers in BF16 mode `in` is the 32-wide im2col buffer)
+ *   out   : device NHWC [N,OH,OW,out_cs], channels [out_coff, out_coff+Cout) written; bf16 unless out_fp32 (FP32 mode: always fp32)
+ *   epi   : 0 none, 1 exp on channel 3 (SCoordNet.py:43), 2 l2-normalise 32 channels (KFNet.py:340; BF16 mode only) */
+KFN_API int kfn_conv_layer(kfn_handle* h, const char* op_key, const void* in, int N, int IH, int IW, int in_cs, void* out,
+                   int OH, int OW, int out_cs, int out_coff, int out_fp32, int epi, void* stream);
+
+/* Number of kernels this library has launched through this handle since the last call (for bench.py's gpu_launches). */
+KFN_API int64_t kfn_launch_count(kfn_handle* h, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KFNET_B200_H_ */

@@ -1,0 +1,79 @@
+// Shared host/device declarations for libkfnet_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/kfnet_b200.h"
+
+namespace kfn {
+
+void set_error(const std::string& msg);
+extern thread_local int64_t g_launches;   // kernels launched by this thread through the library
+
+#define KFN_CUDA_OK(expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      kfn::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                          \
+      return KFN_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+#define KFN_LAUNCH_OK()                                                                            \
+  do {                                                                                             \
+    ++kfn::g_launches;                                                                             \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess) {                                                                       \
+      kfn::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));                     \
+      return KFN_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+#define KFN_REQUIRE(cond, msg)                                                                     \
+  do {                                                                                             \
+    if (!(cond)) {                                                                                 \
+      kfn::set_error(std::string("argument check failed: ") + #cond + " -- " + msg);               \
+      return KFN_ERR_ARG;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// A convolution seen as an implicit GEMM over an "m-grid" of N x MH x MW rows.
+//   input pixel of tap t for row (n,my,mx):  (iy, ix) = (my*istride + dy[t], mx*istride + dx[t]);  zero outside
+//   output pixel:                            (oy, ox) = (my*omul + oaddy,  mx*omul + oaddx)
+// Normal SAME conv: m-grid = output grid, omul=1.  conv2d_transpose phase: m-grid = input grid, omul=2,
+// oadd = phase parity.  Channel stride / offset on the output implement concat-by-construction.
+struct ConvGeom {
+  int N, MH, MW;
+  int IH, IW, in_cs, Cin;
+  int istride;
+  int ntaps;
+  int dy[9], dx[9];
+  int OH, OW, out_cs, out_coff, Cout;
+  int omul, oaddy, oaddx;
+  int relu;
+  int epi;            // EPI_*
+};
+enum { EPI_NONE = 0, EPI_EXP_CH3 = 1, EPI_L2NORM = 2 };
+
+// fp32 CUDA-core implicit GEMM (conv_simt.cu).  weights: [ntaps][Cin][CoutP] fp32, CoutP = roundup(Cout,4).
+int launch_conv_simt(const ConvGeom& g, const float* in, const float* w, int CoutP, const float* bias, float* out,
+                     cudaStream_t st);
+
+// pointwise / gather kernels (pointwise.cu)
+int launch_preprocess_f32(const uint8_t* img, float* out, int64_t n, cudaStream_t st);
+int launch_im2col27_bf16(const uint8_t* img, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st);
+int launch_l2norm32(float* x, int64_t rows, cudaStream_t st);
+int launch_diff_volume(const float* f_prev, const float* f_cur, int NP, int GH, int GW, void* diff, int out_bf16,
+                       cudaStream_t st);
+int launch_softmax_flow(const float* logits, const float* logsig, int logsig_stride, int64_t rows, float* flow,
+                        float* sigma_w, int32_t* argmax, cudaStream_t st);
+int launch_kalman_scan(const float* measure, const float* flow, const float* sigma_w, const float* state_in,
+                       float* state_out, const float* T16_host, int S, int T, int GH, int GW, int first_index,
+                       int reinit_period, int nis_gate, float* out_map, float* temp, float* kf, float* nis,
+                       int32_t* taps, cudaStream_t st);
+
+}  // namespace kfn

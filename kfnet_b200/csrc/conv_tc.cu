@@ -1,0 +1,445 @@
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (KFN_MODE_BF16).
+//
+// GEMM view of one conv (ConvGeom, common.cuh):  D[M, Cout] = sum_{tap, c} A_tap[M, c] * W[tap][Cout][c]
+//   M tile  = 128 m-grid rows = a (bw x bh x bn) box of pixels, bw*bh*bn = 128, chosen per layer on the host;
+//   A tiles = one TMA tiled load per (tap, KC-channel chunk): a 5-D box of the NHWC activation tensor
+//             starting at the tap-shifted pixel; out-of-range coordinates are zero-filled by TMA, which IS the
+//             SAME padding of the reference's tf.layers.conv2d.  Stride-2 convs read a
+//             parity-split 5-D view (c|wpar, w/2, hpar, h/2, n) of the same buffer, so no element strides are needed;
+//   B tiles = [BN x KC] K-major slices of the packed weights [tap][CoutP][Cin];
+//   both land in shared memory in the canonical K-major swizzled layout (128B/64B/32B for KC = 64/32/16 bf16)
+//   that tcgen05.mma consumes through shared-memory descriptors;
+//   accumulators live in TMEM (2 stages x 256 fp32 columns), drained by 4 epilogue warps with tcgen05.ld
+//   while the next tile's MMAs run; bias + ReLU (+ exp / l2-normalise) fused into the epilogue.
+//
+// One persistent CTA per SM (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "conv_tc.h"
+
+namespace kfn {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kMaxStages = 12;
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 512;
+constexpr long long kWatchdogCycles = 4000000000ll;   // ~2 s at 1.9 GHz: trap instead of hanging the GPU
+
+struct __align__(8) TcParams {
+  int tiles_w, tiles_h, tiles_n, n_tiles;
+  int lbw, lbh;                 // log2 of the pixel box (bn = 128 >> (lbw + lbh))
+  int N, MH, MW;
+  int istride, in_cs;
+  int ntaps;
+  int dy[9], dx[9];
+  int kchunks, KC, BN;
+  uint32_t desc_hi;             // upper 32 bits of the UMMA smem descriptor (SBO, version, swizzle mode)
+  uint32_t idesc;
+  int stages;
+  uint32_t stage_bytes, a_bytes, b_bytes;
+  int OH, OW, out_cs, out_coff, Cout, omul, oaddy, oaddx, relu, epi, out_bf16;
+  void* out;
+  const float* bias;            // [CoutP] zero padded
+};
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  const long long t0 = clock64();
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && (clock64() - t0) > kWatchdogCycles) __trap();
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[kMaxStages];
+  __shared__ __align__(8) uint64_t s_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t s_tfull[2];
+  __shared__ __align__(8) uint64_t s_tempty[2];
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&s_tfull[a]), 1);
+      mbar_init(smem_u32(&s_tempty[a]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {   // whole warp: TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int kblocks = p.ntaps * p.kchunks;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (one lane)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int tn = mt / p.tiles_h;
+        const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << (7 - p.lbw - p.lbh);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int dy = p.dy[tap], dx = p.dx[tap];
+          int cw, cpar, chh, coff;
+          if (p.istride == 1) { cw = w0 + dx; cpar = 0; chh = h0 + dy; coff = 0; }
+          else { cw = w0 + (dx >> 1); cpar = dy & 1; chh = h0 + (dy >> 1); coff = (dx & 1) * p.in_cs; }
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);
+            const uint32_t full = smem_u32(&s_full[s]);
+            const uint32_t a_dst = smem_base + (uint32_t)s * p.stage_bytes;
+            mbar_expect_tx(full, p.a_bytes + p.b_bytes);
+            tma_load_5d(a_dst, &tmA, full, coff + kc * p.KC, cw, cpar, chh, n0);
+            tma_load_3d(a_dst + p.a_bytes, &tmB, full, kc * p.KC, nt * p.BN, tap);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int j = 0;
+      const uint64_t desc_hi = (uint64_t)p.desc_hi << 32;
+      const int ksteps = p.KC >> 4;    // UMMA_K = 16 bf16 = 32 bytes
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+        const int a = j & 1;
+        const uint32_t aph = (uint32_t)(j >> 1) & 1u;
+        mbar_wait(smem_u32(&s_tempty[a]), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)a * 256u;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(smem_u32(&s_full[s]), ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + (uint32_t)s * p.stage_bytes;
+          const uint32_t b_addr = a_addr + p.a_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + k * 32) >> 4) & 0x3FFFu) | (1ull << 16);
+            const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFFu) | (1ull << 16);
+            umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&s_empty[s]));       // frees the smem stage once these MMAs retire
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(smem_u32(&s_tfull[a]));          // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (4 warps)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int wi = row & ((1 << p.lbw) - 1);
+    const int hi = (row >> p.lbw) & ((1 << p.lbh) - 1);
+    const int ni = row >> (p.lbw + p.lbh);
+    const int esize = p.out_bf16 ? 2 : 4;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int tn = mt / p.tiles_h;
+      const int n = (tn << (7 - p.lbw - p.lbh)) + ni;
+      const int my = (th << p.lbh) + hi;
+      const int mx = (tw << p.lbw) + wi;
+      const bool valid = n < p.N;
+      const int64_t opix = ((int64_t)n * p.OH + my * p.omul + p.oaddy) * p.OW + mx * p.omul + p.oaddx;
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) + (opix * p.out_cs + p.out_coff) * esize;
+      const int a = j & 1;
+      const uint32_t aph = (uint32_t)(j >> 1) & 1u;
+      mbar_wait(smem_u32(&s_tfull[a]), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)a * 256u;
+      const int col0 = nt * p.BN;
+
+      if (p.epi == EPI_L2NORM) {
+        // feat7: BN == Cout == 32, fp32 output, x * rsqrt(max(sum x^2, 1e-12))  (KFNet/KFNet.py:340)
+        float v[32];
+        tmem_ld16(taddr, v);
+        tmem_ld16(taddr + 16, v + 16);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] += __ldg(p.bias + i); ss += v[i] * v[i]; }
+        const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>(orow);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            dst[q] = make_float4(v[4 * q] * inv, v[4 * q + 1] * inv, v[4 * q + 2] * inv, v[4 * q + 3] * inv);
+        }
+      } else {
+        for (int nc = 0; nc < p.BN; nc += 16) {
+          float v[16];
+          tmem_ld16(taddr + nc, v);
+          const int c = col0 + nc;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = __ldg(b4 + q);
+            v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.epi == EPI_EXP_CH3 && c == 0) v[3] = expf(v[3]);
+          if (!valid) continue;
+          const int nvalid = p.Cout - c;
+          if (p.out_bf16) {
+            uint8_t* dst = orow + (int64_t)c * 2;
+            if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+              uint4 o0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+              uint4 o1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+              reinterpret_cast<uint4*>(dst)[0] = o0;
+              reinterpret_cast<uint4*>(dst)[1] = o1;
+            } else {
+              __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) d[i] = __float2bfloat16(v[i]);
+            }
+          } else {
+            float* d = reinterpret_cast<float*>(orow) + c;
+            if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                reinterpret_cast<float4*>(d)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) d[i] = v[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_tempty[a]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
+int pow2_divisor(int v, int cap) { int d = 1; while (d * 2 <= cap && v % (d * 2) == 0) d *= 2; return d; }
+
+}  // namespace
+
+int tc_pick_kc(int Cin) { return (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16; }
+int tc_cout_padded(int Cout) { return (Cout + 15) / 16 * 16; }
+
+int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int CoutP, const float* bias_padded,
+                    void* out, int out_bf16, int num_sms, TcConvPlan* plan) {
+  PFN_encodeTiled encode = get_encode();
+  if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found (no CUDA driver?)"); return KFN_ERR_CUDA; }
+  KFN_REQUIRE(g.Cin % 16 == 0, "tensor-core conv needs Cin % 16 == 0");
+  KFN_REQUIRE(g.in_cs % 8 == 0, "input channel stride must keep pixels 16-byte aligned");
+  KFN_REQUIRE(CoutP % 16 == 0 && (CoutP <= 256 || CoutP % 256 == 0), "CoutP must be 16..256 (mult of 16) or k*256");
+  KFN_REQUIRE(g.istride == 1 || (g.istride == 2 && g.IH % 2 == 0 && g.IW % 2 == 0), "stride must be 1 or 2 (even input)");
+  KFN_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
+              "TMA needs 16-byte aligned global addresses");
+  static_assert(sizeof(TcParams) + 2 * sizeof(CUtensorMap) <= sizeof(TcConvPlan::blob), "TcConvPlan blob too small");
+
+  CUtensorMap* tmA = reinterpret_cast<CUtensorMap*>(plan->blob);
+  CUtensorMap* tmB = tmA + 1;
+  TcParams& p = *reinterpret_cast<TcParams*>(tmB + 1);
+  memset(plan->blob, 0, sizeof(plan->blob));
+
+  const int KC = tc_pick_kc(g.Cin);
+  const int BN = CoutP < 256 ? CoutP : 256;
+  const int bw = pow2_divisor(g.MW, 128);
+  const int bh = pow2_divisor(g.MH, 128 / bw);
+  const int bn = 128 / (bw * bh);
+  p.lbw = ilog2(bw); p.lbh = ilog2(bh);
+  p.tiles_w = g.MW / bw; p.tiles_h = g.MH / bh; p.tiles_n = (g.N + bn - 1) / bn;
+  p.n_tiles = CoutP / BN;
+  p.N = g.N; p.MH = g.MH; p.MW = g.MW;
+  p.istride = g.istride; p.in_cs = g.in_cs;
+  p.ntaps = g.ntaps;
+  for (int t = 0; t < g.ntaps; ++t) { p.dy[t] = g.dy[t]; p.dx[t] = g.dx[t]; }
+  p.kchunks = g.Cin / KC; p.KC = KC; p.BN = BN;
+  const int row_bytes = KC * 2;                       // == swizzle span
+  const uint32_t layout_type = (KC == 64) ? 2u : (KC == 32) ? 4u : 6u;   // SWIZZLE_128B / 64B / 32B
+  const uint32_t sbo16 = (uint32_t)(8 * row_bytes) >> 4;
+  p.desc_hi = sbo16 | (1u << 14) | (layout_type << 29);   // bits 32-45 SBO, 46 version=1, 61-63 layout
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  p.a_bytes = (uint32_t)(kBlockM * row_bytes);
+  p.b_bytes = (uint32_t)(BN * row_bytes);
+  p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
+  const uint32_t budget = 200 * 1024;
+  int stages = (int)(budget / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  KFN_REQUIRE(stages >= 2, "pipeline needs at least 2 stages");
+  p.stages = stages;
+  p.OH = g.OH; p.OW = g.OW; p.out_cs = g.out_cs; p.out_coff = g.out_coff; p.Cout = g.Cout;
+  p.omul = g.omul; p.oaddy = g.oaddy; p.oaddx = g.oaddx; p.relu = g.relu; p.epi = g.epi; p.out_bf16 = out_bf16;
+  p.out = out; p.bias = bias_padded;
+  if (g.epi == EPI_L2NORM) KFN_REQUIRE(BN == 32 && g.Cout == 32 && !out_bf16 && g.out_cs % 4 == 0, "l2norm epilogue shape");
+
+  const CUtensorMapSwizzle swz = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : (KC == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  // ---- A: 5-D view of the NHWC bf16 activation buffer
+  cuuint64_t dimA[5], strA[4];
+  cuuint32_t boxA[5] = {(cuuint32_t)KC, (cuuint32_t)bw, 1u, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  const cuuint64_t cs = (cuuint64_t)g.in_cs * 2;      // bytes per pixel
+  if (g.istride == 1) {
+    dimA[0] = g.Cin; dimA[1] = g.IW; dimA[2] = 1; dimA[3] = g.IH; dimA[4] = g.N;
+    strA[0] = cs; strA[1] = cs * g.IW; strA[2] = cs * g.IW; strA[3] = cs * g.IW * g.IH;
+  } else {
+    dimA[0] = (cuuint64_t)g.in_cs + g.Cin; dimA[1] = g.IW / 2; dimA[2] = 2; dimA[3] = g.IH / 2; dimA[4] = g.N;
+    strA[0] = cs * 2; strA[1] = cs * g.IW; strA[2] = cs * g.IW * 2; strA[3] = cs * g.IW * g.IH;
+  }
+  CUresult r = encode(tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dimA, strA, boxA, ones,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r)); return KFN_ERR_CUDA; }
+  // ---- B: packed weights [tap][CoutP][Cin]
+  cuuint64_t dimB[3] = {(cuuint64_t)g.Cin, (cuuint64_t)CoutP, (cuuint64_t)g.ntaps};
+  cuuint64_t strB[2] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Cin * 2 * CoutP};
+  cuuint32_t boxB[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1u};
+  r = encode(tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dimB, strB, boxB, ones,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); return KFN_ERR_CUDA; }
+
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  plan->grid = total_tiles < num_sms ? total_tiles : num_sms;
+  plan->smem = (size_t)p.stages * p.stage_bytes + 1024;
+  return KFN_OK;
+}
+
+int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024 + 1024));
+    attr_set = true;
+  }
+  const CUtensorMap* tmA = reinterpret_cast<const CUtensorMap*>(plan.blob);
+  const TcParams& p = *reinterpret_cast<const TcParams*>(tmA + 2);
+  conv_tc_kernel<<<plan.grid, kThreads, plan.smem, st>>>(tmA[0], tmA[1], p);
+  KFN_LAUNCH_OK();
+  return KFN_OK;
+}
+
+}  // namespace kfn

@@ -1,0 +1,22 @@
+// Host interface of the tcgen05/TMA implicit-GEMM convolution (conv_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace kfn {
+
+// Opaque launch plan: two CUtensorMaps (activation view, packed weights) + kernel parameters.
+struct TcConvPlan {
+  alignas(64) uint8_t blob[768];
+  int grid;
+  size_t smem;
+};
+
+int tc_pick_kc(int Cin);          // channels per k-block: 64 / 32 / 16 (128B / 64B / 32B swizzle)
+int tc_cout_padded(int Cout);     // weights are packed [tap][CoutP][Cin] bf16 with CoutP = roundup(Cout, 16)
+
+// in: bf16 NHWC activations; w_packed: bf16 [ntaps][CoutP][Cin]; bias_padded: fp32 [CoutP]; out: bf16 or fp32.
+int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int CoutP, const float* bias_padded,
+                    void* out, int out_bf16, int num_sms, TcConvPlan* plan);
+int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st);
+
+}  // namespace kfn

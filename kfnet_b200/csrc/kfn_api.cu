@@ -1,0 +1,577 @@
+// C ABI of libkfnet_b200.so: handle, weights, workspace arena and the layer schedules of SCoordNet,
+// the OFlowNet feature tower, the OFlowNet U-Net + FC head, and the batched sequence evaluation.
+// See include/kfnet_b200.h for the contract and the reference functions each entry point replaces.
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_tc.h"
+
+namespace kfn {
+thread_local std::string g_error;
+thread_local int64_t g_launches = 0;
+void set_error(const std::string& msg) { g_error = msg; }
+}  // namespace kfn
+
+using namespace kfn;
+
+namespace {
+
+enum Kind { CONV = 0, DECONV = 1, DENSE = 2 };
+struct LayerSpec { const char* scope; const char* name; Kind kind; int k, cin, cout, stride; bool relu; };
+
+// cnn_wrapper/SCoordNet.py:21-32, KFNet/KFNet.py:318-338, cnn_wrapper/OFlowNet.py:19-41,50-55
+const LayerSpec kLayers[] = {
+    {"ScoreNet", "conv1a", CONV, 3, 3, 64, 1, true},      {"ScoreNet", "conv1b", CONV, 3, 64, 64, 1, true},
+    {"ScoreNet", "conv2a", CONV, 3, 64, 256, 2, true},    {"ScoreNet", "conv2b", CONV, 3, 256, 256, 1, true},
+    {"ScoreNet", "conv3a", CONV, 3, 256, 512, 2, true},   {"ScoreNet", "conv3b", CONV, 3, 512, 512, 1, true},
+    {"ScoreNet", "conv4a", CONV, 3, 512, 1024, 2, true},  {"ScoreNet", "conv4b", CONV, 3, 1024, 1024, 1, true},
+    {"ScoreNet", "conv5", CONV, 3, 1024, 512, 1, true},   {"ScoreNet", "conv6", CONV, 3, 512, 256, 1, true},
+    {"ScoreNet", "conv7", CONV, 1, 256, 128, 1, true},    {"ScoreNet", "prediction", CONV, 1, 128, 4, 1, false},
+    {"Temporal", "feat1", CONV, 3, 3, 16, 1, true},       {"Temporal", "feat2", CONV, 3, 16, 32, 2, true},
+    {"Temporal", "feat3", CONV, 3, 32, 32, 1, true},      {"Temporal", "feat4", CONV, 3, 32, 64, 2, true},
+    {"Temporal", "feat5", CONV, 3, 64, 64, 1, true},      {"Temporal", "feat6", CONV, 3, 64, 128, 2, true},
+    {"Temporal", "feat7", CONV, 3, 128, 32, 1, false},
+    {"Temporal", "conv0", CONV, 3, 32, 32, 1, true},      {"Temporal", "conv1a", CONV, 3, 32, 32, 2, true},
+    {"Temporal", "conv1b", CONV, 3, 32, 32, 1, true},     {"Temporal", "conv2a", CONV, 3, 32, 64, 2, true},
+    {"Temporal", "conv2b", CONV, 3, 64, 64, 1, true},     {"Temporal", "conv3a", CONV, 3, 64, 128, 2, true},
+    {"Temporal", "conv3b", CONV, 3, 128, 128, 1, true},   {"Temporal", "upconv2", DECONV, 3, 128, 64, 2, true},
+    {"Temporal", "conv4", CONV, 3, 128, 64, 1, true},     {"Temporal", "upconv1", DECONV, 3, 64, 32, 2, true},
+    {"Temporal", "conv5", CONV, 3, 64, 32, 1, true},      {"Temporal", "upconv0", DECONV, 3, 32, 16, 2, true},
+    {"Temporal", "conv6", CONV, 3, 48, 16, 1, true},      {"Temporal", "prediction", CONV, 3, 16, 1, 1, false},
+    {"Temporal", "fc1", DENSE, 1, 128, 64, 1, true},      {"Temporal", "fc2", DENSE, 1, 64, 32, 1, true},
+    {"Temporal", "uncertainty", DENSE, 1, 32, 1, 1, false},
+};
+constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
+
+const LayerSpec* find_layer(const std::string& scope_name) {
+  for (int i = 0; i < kNumLayers; ++i)
+    if (scope_name == std::string(kLayers[i].scope) + "/" + kLayers[i].name) return &kLayers[i];
+  return nullptr;
+}
+
+// One packed GEMM operand: a conv, one phase of a conv2d_transpose, a dense layer, or the im2col'ed first layer.
+struct PackedOp {
+  void* w = nullptr;       // fp32 [ntaps][Cin][CoutP] (FP32 mode) or bf16 [ntaps][CoutP][Cin] (BF16 mode)
+  float* bias = nullptr;   // fp32 [CoutP], zero padded
+  int Cin = 0, Cout = 0, CoutP = 0;
+  int ntaps = 0, dy[9] = {0}, dx[9] = {0};
+  int stride = 1, relu = 0;
+};
+
+struct Arena {
+  uint8_t* base; int64_t size; int64_t off = 0; bool overflow = false;
+  Arena(void* b, int64_t s) : base(reinterpret_cast<uint8_t*>(b)), size(s) {}
+  void* alloc(int64_t bytes) {
+    off = (off + 1023) & ~int64_t(1023);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    if (base && off > size) overflow = true;
+    return p;
+  }
+};
+
+struct Act { void* p; int N, H, W, C; };   // NHWC view, C = channel stride of the buffer
+
+}  // namespace
+
+struct kfn_handle {
+  int device = 0, mode = 0, H = 0, W = 0, GH = 0, GW = 0, num_sms = 148;
+  std::map<std::string, std::vector<float>> host_w;
+  std::map<std::string, PackedOp> ops;
+  std::vector<void*> allocs;
+  std::map<std::tuple<std::string, const void*, void*, int>, TcConvPlan> plans;
+  bool finalized = false;
+};
+
+namespace {
+
+int esize(const kfn_handle* h) { return h->mode == KFN_MODE_BF16 ? 2 : 4; }
+
+// tap valid iff some m-grid row reads an in-range input pixel through it
+bool tap_live(int d, int M, int stride, int I) {
+  for (int m = 0; m < M; ++m) { int i = m * stride + d; if (i >= 0 && i < I) return true; }
+  return false;
+}
+
+// Builds the packed operand `key` from TF-layout host weights.
+//   kind CONV   : taps (ky,kx) with (dy,dx) = (ky - pad, kx - pad), pad = (k==3 && stride==1) ? 1 : 0  (SAME, App. A.2)
+//   kind DECONV : phase (py,px): ky in {0 (dy=0), 2 (dy=-1)} for py==0, ky=1 (dy=0) for py==1  (App. A.3)
+//   first_layer : 3x3xCin=3 conv as one tap over the 32-wide im2col row, 0.00625 folded in (BF16 mode only)
+int pack_op(kfn_handle* h, const std::string& key, const LayerSpec& L, int phase, bool first_layer_im2col, int MH,
+            int MW, int IH, int IW) {
+  const std::string base = std::string(L.scope) + "/" + L.name;
+  auto itw = h->host_w.find(base + "/kernel");
+  auto itb = h->host_w.find(base + "/bias");
+  if (itw == h->host_w.end() || itb == h->host_w.end()) { set_error("missing weight " + base); return KFN_ERR_ARG; }
+  const float* w = itw->second.data();
+  const float* b = itb->second.data();
+  PackedOp op;
+  op.Cout = L.cout; op.relu = L.relu ? 1 : 0; op.stride = (L.kind == CONV) ? L.stride : 1;
+  // (ky, kx, dy, dx) list
+  struct Tap { int ky, kx, dy, dx; };
+  std::vector<Tap> taps;
+  if (first_layer_im2col) {
+    op.Cin = 32; taps.push_back({0, 0, 0, 0});
+  } else if (L.kind == DENSE || L.k == 1) {
+    op.Cin = L.cin; taps.push_back({0, 0, 0, 0});
+  } else if (L.kind == CONV) {
+    op.Cin = L.cin;
+    const int pad = (L.stride == 1) ? 1 : 0;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx)
+        if (tap_live(ky - pad, MH, L.stride, IH) && tap_live(kx - pad, MW, L.stride, IW))
+          taps.push_back({ky, kx, ky - pad, kx - pad});
+  } else {   // DECONV phase
+    op.Cin = L.cin;
+    const int py = phase >> 1, px = phase & 1;
+    const int kys[2] = {py ? 1 : 0, 2}, dys[2] = {0, -1};
+    const int kxs[2] = {px ? 1 : 0, 2}, dxs[2] = {0, -1};
+    for (int a = 0; a < (py ? 1 : 2); ++a)
+      for (int c = 0; c < (px ? 1 : 2); ++c)
+        if (tap_live(dys[a], MH, 1, IH) && tap_live(dxs[c], MW, 1, IW)) taps.push_back({kys[a], kxs[c], dys[a], dxs[c]});
+  }
+  op.ntaps = (int)taps.size();
+  if (op.ntaps == 0 || op.ntaps > 9) { set_error("bad tap count for " + key); return KFN_ERR_ARG; }
+  for (int t = 0; t < op.ntaps; ++t) { op.dy[t] = taps[t].dy; op.dx[t] = taps[t].dx; }
+  const bool bf16 = h->mode == KFN_MODE_BF16;
+  op.CoutP = bf16 ? tc_cout_padded(L.cout) : (L.cout + 3) / 4 * 4;
+
+  // element (tap t, ci, co) of the logical [taps][Cin][Cout] operand
+  auto W = [&](int t, int ci, int co) -> float {
+    const Tap& tp = taps[t];
+    if (first_layer_im2col) {
+      if (ci >= 27) return 0.f;
+      const int ky = ci / 9, kx = (ci / 3) % 3, c = ci % 3;
+      return w[((ky * 3 + kx) * 3 + c) * L.cout + co] * 0.00625f;
+    }
+    if (L.kind == DENSE) return w[ci * L.cout + co];
+    if (L.kind == CONV) return w[((tp.ky * L.k + tp.kx) * L.cin + ci) * L.cout + co];
+    return w[((tp.ky * 3 + tp.kx) * L.cout + co) * L.cin + ci];   // DECONV [kh,kw,Cout,Cin]
+  };
+  const size_t nelem = (size_t)op.ntaps * op.Cin * op.CoutP;
+  std::vector<float> biasp(op.CoutP, 0.f);
+  for (int co = 0; co < L.cout; ++co) biasp[co] = b[co];
+  KFN_CUDA_OK(cudaMalloc(&op.bias, op.CoutP * sizeof(float)));
+  h->allocs.push_back(op.bias);
+  KFN_CUDA_OK(cudaMemcpy(op.bias, biasp.data(), op.CoutP * sizeof(float), cudaMemcpyHostToDevice));
+  if (!bf16) {
+    std::vector<float> pk(nelem, 0.f);
+    for (int t = 0; t < op.ntaps; ++t)
+      for (int ci = 0; ci < op.Cin; ++ci)
+        for (int co = 0; co < L.cout; ++co) pk[((size_t)t * op.Cin + ci) * op.CoutP + co] = W(t, ci, co);
+    KFN_CUDA_OK(cudaMalloc(&op.w, nelem * sizeof(float)));
+    h->allocs.push_back(op.w);
+    KFN_CUDA_OK(cudaMemcpy(op.w, pk.data(), nelem * sizeof(float), cudaMemcpyHostToDevice));
+  } else {
+    std::vector<__nv_bfloat16> pk(nelem, __float2bfloat16(0.f));
+    for (int t = 0; t < op.ntaps; ++t)
+      for (int co = 0; co < L.cout; ++co)
+        for (int ci = 0; ci < op.Cin; ++ci)
+          pk[((size_t)t * op.CoutP + co) * op.Cin + ci] = __float2bfloat16(W(t, ci, co));
+    KFN_CUDA_OK(cudaMalloc(&op.w, nelem * sizeof(__nv_bfloat16)));
+    h->allocs.push_back(op.w);
+    KFN_CUDA_OK(cudaMemcpy(op.w, pk.data(), nelem * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  }
+  h->ops[key] = op;
+  return KFN_OK;
+}
+
+// Runs packed op `key`: in (NHWC, `in.C` channel stride, op.Cin channels read from channel 0 of `in.p`)
+// -> out channels [out_coff, out_coff + Cout) of `out` at pixel (my*omul + oaddy, mx*omul + oaddx).
+int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff, int MH, int MW, int omul, int oaddy,
+           int oaddx, int epi, bool out_fp32, cudaStream_t st) {
+  auto it = h->ops.find(key);
+  if (it == h->ops.end()) { set_error("unknown op " + key); return KFN_ERR_STATE; }
+  const PackedOp& op = it->second;
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = in.N; g.MH = MH; g.MW = MW;
+  g.IH = in.H; g.IW = in.W; g.in_cs = in.C; g.Cin = op.Cin;
+  g.istride = op.stride;
+  g.ntaps = op.ntaps;
+  for (int t = 0; t < op.ntaps; ++t) { g.dy[t] = op.dy[t]; g.dx[t] = op.dx[t]; }
+  g.OH = out.H; g.OW = out.W; g.out_cs = out.C; g.out_coff = out_coff; g.Cout = op.Cout;
+  g.omul = omul; g.oaddy = oaddy; g.oaddx = oaddx; g.relu = op.relu; g.epi = epi;
+  if (h->mode == KFN_MODE_FP32) {
+    return launch_conv_simt(g, reinterpret_cast<const float*>(in.p), reinterpret_cast<const float*>(op.w), op.CoutP,
+                            op.bias, reinterpret_cast<float*>(out.p), st);
+  }
+  auto pk = std::make_tuple(key, (const void*)in.p, out.p, in.N);
+  auto pit = h->plans.find(pk);
+  if (pit == h->plans.end()) {
+    TcConvPlan plan;
+    int rc = prepare_conv_tc(g, in.p, op.w, op.CoutP, op.bias, out.p, out_fp32 ? 0 : 1, h->num_sms, &plan);
+    if (rc != KFN_OK) { set_error(key + ": " + g_error); return rc; }
+    if (h->plans.size() > 4096) h->plans.clear();
+    pit = h->plans.emplace(pk, plan).first;
+  }
+  return launch_conv_tc(pit->second, st);
+}
+
+// plain conv: m-grid == output grid
+int conv(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff, int epi, bool out_fp32, cudaStream_t st) {
+  return run_op(h, key, in, out, out_coff, out.H, out.W, 1, 0, 0, epi, out_fp32, st);
+}
+// conv2d_transpose k3 s2 SAME = 4 sub-pixel phase convs over the input grid
+int deconv(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff, cudaStream_t st) {
+  for (int ph = 0; ph < 4; ++ph) {
+    int rc = run_op(h, key + "#p" + std::to_string(ph), in, out, out_coff, in.H, in.W, 2, ph >> 1, ph & 1, EPI_NONE,
+                    false, st);
+    if (rc != KFN_OK) return rc;
+  }
+  return KFN_OK;
+}
+
+Act act(void* p, int N, int H, int W, int C) { return Act{p, N, H, W, C}; }
+void* offs(void* p, int64_t elems, int es) { return p ? reinterpret_cast<uint8_t*>(p) + elems * es : nullptr; }
+
+// ---------------------------------------------------------------------------------------------
+int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, Arena& ar, cudaStream_t st, bool dry) {
+  const int H = h->H, W = h->W, es = esize(h);
+  const int64_t px = (int64_t)B * H * W;
+  void* pre = ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
+  void* bufA = ar.alloc(px * 64 * es);
+  void* bufB = ar.alloc(px * 64 * es);
+  if (dry) return KFN_OK;
+  if (ar.overflow) { set_error("workspace too small for scoordnet_forward"); return KFN_ERR_WORKSPACE; }
+  int rc;
+  if (h->mode == KFN_MODE_FP32) {
+    if ((rc = launch_preprocess_f32(images, (float*)pre, px * 3, st))) return rc;
+    if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 3), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
+  } else {
+    if ((rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
+    if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 32), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
+  }
+  struct Step { const char* name; int div; int c; };
+  const Step steps[] = {{"conv1b", 1, 64},  {"conv2a", 2, 256}, {"conv2b", 2, 256}, {"conv3a", 4, 512}, {"conv3b", 4, 512},
+                        {"conv4a", 8, 1024}, {"conv4b", 8, 1024}, {"conv5", 8, 512}, {"conv6", 8, 256}, {"conv7", 8, 128}};
+  Act cur = act(bufA, B, H, W, 64);
+  void* nextbuf = bufB;
+  for (const Step& s : steps) {
+    Act nxt = act(nextbuf, B, H / s.div, W / s.div, s.c);
+    if ((rc = conv(h, std::string("ScoreNet/") + s.name, cur, nxt, 0, EPI_NONE, false, st))) return rc;
+    nextbuf = cur.p; cur = nxt;
+  }
+  // prediction (no ReLU) + exp on channel 3 -> (coord xyz, sigma_z)   SCoordNet.py:32,39-44
+  return conv(h, "ScoreNet/prediction", cur, act(measure, B, H / 8, W / 8, 4), 0, EPI_EXP_CH3, true, st);
+}
+
+int tower_impl(kfn_handle* h, const uint8_t* images, int B, float* feat, Arena& ar, cudaStream_t st, bool dry) {
+  const int H = h->H, W = h->W, es = esize(h);
+  const int64_t px = (int64_t)B * H * W;
+  void* pre = ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
+  void* bufA = ar.alloc(px * 16 * es);
+  void* bufB = ar.alloc(px * 16 * es);
+  if (dry) return KFN_OK;
+  if (ar.overflow) { set_error("workspace too small for oflow_feat_forward"); return KFN_ERR_WORKSPACE; }
+  int rc;
+  if (h->mode == KFN_MODE_FP32) {
+    if ((rc = launch_preprocess_f32(images, (float*)pre, px * 3, st))) return rc;
+    if ((rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 3), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
+  } else {
+    if ((rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
+    if ((rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 32), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
+  }
+  struct Step { const char* name; int div; int c; };
+  const Step steps[] = {{"feat2", 2, 32}, {"feat3", 2, 32}, {"feat4", 4, 64}, {"feat5", 4, 64}, {"feat6", 8, 128}};
+  Act cur = act(bufA, B, H, W, 16);
+  void* nextbuf = bufB;
+  for (const Step& s : steps) {
+    Act nxt = act(nextbuf, B, H / s.div, W / s.div, s.c);
+    if ((rc = conv(h, std::string("Temporal/") + s.name, cur, nxt, 0, EPI_NONE, false, st))) return rc;
+    nextbuf = cur.p; cur = nxt;
+  }
+  Act out = act(feat, B, H / 8, W / 8, 32);
+  if (h->mode == KFN_MODE_FP32) {
+    if ((rc = conv(h, "Temporal/feat7", cur, out, 0, EPI_NONE, true, st))) return rc;
+    return launch_l2norm32(feat, (int64_t)B * (H / 8) * (W / 8), st);
+  }
+  return conv(h, "Temporal/feat7", cur, out, 0, EPI_L2NORM, true, st);
+}
+
+int oflownet_impl(kfn_handle* h, const float* f_prev, const float* f_cur, int NP, float* flow, float* sigma_w,
+                  float* logits_out, int32_t* argmax, Arena& ar, cudaStream_t st, bool dry) {
+  const int es = esize(h);
+  const int64_t R64 = (int64_t)NP * h->GH * h->GW;
+  const int R = (int)R64;
+  void* diff = ar.alloc(R64 * 64 * 32 * es);
+  void* cat0 = ar.alloc(R64 * 64 * 48 * es);   // [upconv0 (16) | conv0 (32)]     OFlowNet.py:38-39
+  void* c1a = ar.alloc(R64 * 16 * 32 * es);
+  void* cat1 = ar.alloc(R64 * 16 * 64 * es);   // [upconv1 (32) | conv1b (32)]    OFlowNet.py:33-34
+  void* c2a = ar.alloc(R64 * 4 * 64 * es);
+  void* cat2 = ar.alloc(R64 * 4 * 128 * es);   // [upconv2 (64) | conv2b (64)]    OFlowNet.py:28-29
+  void* c3a = ar.alloc(R64 * 128 * es);
+  void* c3b = ar.alloc(R64 * 128 * es);
+  void* c4 = ar.alloc(R64 * 4 * 64 * es);
+  void* c5 = ar.alloc(R64 * 16 * 32 * es);
+  void* c6 = ar.alloc(R64 * 64 * 16 * es);
+  void* fc1 = ar.alloc(R64 * 64 * es);
+  void* fc2 = ar.alloc(R64 * 32 * es);
+  float* unc = (float*)ar.alloc(R64 * 4);
+  float* logits = logits_out ? logits_out : (float*)ar.alloc(R64 * 64 * 4);
+  if (dry) return KFN_OK;
+  if (ar.overflow) { set_error("workspace too small for oflownet_forward"); return KFN_ERR_WORKSPACE; }
+  int rc;
+  if ((rc = launch_diff_volume(f_prev, f_cur, NP, h->GH, h->GW, diff, h->mode == KFN_MODE_BF16, st))) return rc;
+  const std::string T = "Temporal/";
+#define RUN(x) if ((rc = (x))) return rc
+  RUN(conv(h, T + "conv0", act(diff, R, 8, 8, 32), act(cat0, R, 8, 8, 48), 16, EPI_NONE, false, st));
+  RUN(conv(h, T + "conv1a", act(offs(cat0, 16, es), R, 8, 8, 48), act(c1a, R, 4, 4, 32), 0, EPI_NONE, false, st));
+  RUN(conv(h, T + "conv1b", act(c1a, R, 4, 4, 32), act(cat1, R, 4, 4, 64), 32, EPI_NONE, false, st));
+  RUN(conv(h, T + "conv2a", act(offs(cat1, 32, es), R, 4, 4, 64), act(c2a, R, 2, 2, 64), 0, EPI_NONE, false, st));
+  RUN(conv(h, T + "conv2b", act(c2a, R, 2, 2, 64), act(cat2, R, 2, 2, 128), 64, EPI_NONE, false, st));
+  RUN(conv(h, T + "conv3a", act(offs(cat2, 64, es), R, 2, 2, 128), act(c3a, R, 1, 1, 128), 0, EPI_NONE, false, st));
+  RUN(conv(h, T + "conv3b", act(c3a, R, 1, 1, 128), act(c3b, R, 1, 1, 128), 0, EPI_NONE, false, st));
+  RUN(deconv(h, T + "upconv2", act(c3b, R, 1, 1, 128), act(cat2, R, 2, 2, 128), 0, st));
+  RUN(conv(h, T + "conv4", act(cat2, R, 2, 2, 128), act(c4, R, 2, 2, 64), 0, EPI_NONE, false, st));
+  RUN(deconv(h, T + "upconv1", act(c4, R, 2, 2, 64), act(cat1, R, 4, 4, 64), 0, st));
+  RUN(conv(h, T + "conv5", act(cat1, R, 4, 4, 64), act(c5, R, 4, 4, 32), 0, EPI_NONE, false, st));
+  RUN(deconv(h, T + "upconv0", act(c5, R, 4, 4, 32), act(cat0, R, 8, 8, 48), 0, st));
+  RUN(conv(h, T + "conv6", act(cat0, R, 8, 8, 48), act(c6, R, 8, 8, 16), 0, EPI_NONE, false, st));
+  RUN(conv(h, T + "prediction", act(c6, R, 8, 8, 16), act(logits, R, 8, 8, 1), 0, EPI_NONE, true, st));
+  RUN(conv(h, T + "fc1", act(c3b, R, 1, 1, 128), act(fc1, R, 1, 1, 64), 0, EPI_NONE, false, st));
+  RUN(conv(h, T + "fc2", act(fc1, R, 1, 1, 64), act(fc2, R, 1, 1, 32), 0, EPI_NONE, false, st));
+  RUN(conv(h, T + "uncertainty", act(fc2, R, 1, 1, 32), act(unc, R, 1, 1, 1), 0, EPI_NONE, true, st));
+#undef RUN
+  return launch_softmax_flow(logits, unc, 1, R64, flow, sigma_w, argmax, st);
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* kfn_version(void) { return "kfnet_b200 0.1 (sm_100a)"; }
+const char* kfn_last_error(void) { return kfn::g_error.c_str(); }
+
+int kfn_create(kfn_handle** out, int device, int mode, int image_h, int image_w) {
+  KFN_REQUIRE(out != nullptr, "null out");
+  KFN_REQUIRE(mode == KFN_MODE_FP32 || mode == KFN_MODE_BF16, "unknown mode");
+  KFN_REQUIRE(image_h > 0 && image_w > 0 && image_h % 8 == 0 && image_w % 8 == 0, "image size must be a multiple of 8");
+  int ndev = 0;
+  KFN_CUDA_OK(cudaGetDeviceCount(&ndev));
+  KFN_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this library has no CPU fallback)");
+  KFN_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  KFN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) { set_error("libkfnet_b200 is built for sm_100a only; found sm_" + std::to_string(prop.major * 10 + prop.minor)); return KFN_ERR_CUDA; }
+  kfn_handle* h = new kfn_handle();
+  h->device = device; h->mode = mode; h->H = image_h; h->W = image_w; h->GH = image_h / 8; h->GW = image_w / 8;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return KFN_OK;
+}
+
+int kfn_destroy(kfn_handle* h) {
+  if (!h) return KFN_OK;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+  return KFN_OK;
+}
+
+int kfn_load_weight(kfn_handle* h, const char* name, const float* data, const int64_t* dims, int ndim) {
+  KFN_REQUIRE(h && name && data && dims, "null argument");
+  std::string nm(name);
+  size_t cut = nm.rfind('/');
+  KFN_REQUIRE(cut != std::string::npos, "weight name must be <scope>/<layer>/{kernel,bias}");
+  const LayerSpec* L = find_layer(nm.substr(0, cut));
+  const std::string what = nm.substr(cut + 1);
+  KFN_REQUIRE(L != nullptr, ("unknown layer in " + nm).c_str());
+  int64_t expect[4]; int en = 0;
+  if (what == "bias") { expect[0] = L->cout; en = 1; }
+  else if (what == "kernel") {
+    if (L->kind == CONV) { expect[0] = L->k; expect[1] = L->k; expect[2] = L->cin; expect[3] = L->cout; en = 4; }
+    else if (L->kind == DECONV) { expect[0] = L->k; expect[1] = L->k; expect[2] = L->cout; expect[3] = L->cin; en = 4; }
+    else { expect[0] = L->cin; expect[1] = L->cout; en = 2; }
+  } else { set_error("weight name must end in /kernel or /bias: " + nm); return KFN_ERR_ARG; }
+  KFN_REQUIRE(ndim == en, ("rank mismatch for " + nm).c_str());
+  int64_t n = 1;
+  for (int i = 0; i < en; ++i) { KFN_REQUIRE(dims[i] == expect[i], ("shape mismatch for " + nm).c_str()); n *= dims[i]; }
+  h->host_w[nm].assign(data, data + n);
+  h->finalized = false;
+  return KFN_OK;
+}
+
+int kfn_finalize_weights(kfn_handle* h) {
+  KFN_REQUIRE(h, "null handle");
+  KFN_CUDA_OK(cudaSetDevice(h->device));
+  for (void* p : h->allocs) cudaFree(p);
+  h->allocs.clear(); h->ops.clear(); h->plans.clear();
+  const bool bf16 = h->mode == KFN_MODE_BF16;
+  // spatial dims (output m-grid MH x MW, input IH x IW) of every layer, for tap pruning
+  int rc;
+  int sh = h->H, sw = h->W;   // running SCoordNet / tower resolution
+  for (int i = 0; i < kNumLayers; ++i) {
+    const LayerSpec& L = kLayers[i];
+    const std::string key = std::string(L.scope) + "/" + L.name;
+    const std::string nm(L.name);
+    if (std::string(L.scope) == "ScoreNet" || nm.rfind("feat", 0) == 0) {
+      if (nm == "conv1a" || nm == "feat1") { sh = h->H; sw = h->W; }
+      const int ih = sh, iw = sw;
+      if (L.stride == 2) { sh /= 2; sw /= 2; }
+      const bool first = bf16 && L.cin == 3;
+      if ((rc = pack_op(h, key, L, 0, first, sh, sw, ih, iw))) return rc;
+      continue;
+    }
+    // U-Net: fixed 8x8 windows
+    int ih = 8, oh = 8;
+    if (nm == "conv0" || nm == "conv6" || nm == "prediction") { ih = 8; oh = 8; }
+    else if (nm == "conv1a") { ih = 8; oh = 4; }
+    else if (nm == "conv1b" || nm == "conv5") { ih = 4; oh = 4; }
+    else if (nm == "conv2a") { ih = 4; oh = 2; }
+    else if (nm == "conv2b" || nm == "conv4") { ih = 2; oh = 2; }
+    else if (nm == "conv3a") { ih = 2; oh = 1; }
+    else if (nm == "conv3b") { ih = 1; oh = 1; }
+    else if (nm == "upconv2") { ih = 1; oh = 1; }   // phases run over the INPUT grid
+    else if (nm == "upconv1") { ih = 2; oh = 2; }
+    else if (nm == "upconv0") { ih = 4; oh = 4; }
+    else { ih = 1; oh = 1; }                        // fc1, fc2, uncertainty
+    if (L.kind == DECONV) {
+      for (int ph = 0; ph < 4; ++ph)
+        if ((rc = pack_op(h, key + "#p" + std::to_string(ph), L, ph, false, oh, oh, ih, ih))) return rc;
+    } else {
+      if ((rc = pack_op(h, key, L, 0, false, oh, oh, ih, ih))) return rc;
+    }
+  }
+  h->finalized = true;
+  return KFN_OK;
+}
+
+int64_t kfn_workspace_bytes(kfn_handle* h, int frames, int pairs) {
+  if (!h || frames < 0 || pairs < 0) return KFN_ERR_ARG;
+  int64_t need = 0;
+  if (frames > 0) {
+    Arena a(nullptr, 0); scoordnet_impl(h, nullptr, frames, nullptr, a, nullptr, true); need = a.off > need ? a.off : need;
+    Arena b(nullptr, 0); tower_impl(h, nullptr, frames, nullptr, b, nullptr, true); need = b.off > need ? b.off : need;
+  }
+  if (pairs > 0) {
+    Arena c(nullptr, 0); oflownet_impl(h, nullptr, nullptr, pairs, nullptr, nullptr, nullptr, nullptr, c, nullptr, true);
+    need = c.off > need ? c.off : need;
+  }
+  return need + 4096;
+}
+
+#define KFN_READY(h) do { KFN_REQUIRE(h, "null handle"); if (!h->finalized) { set_error("call kfn_finalize_weights first"); return KFN_ERR_STATE; } KFN_CUDA_OK(cudaSetDevice(h->device)); } while (0)
+
+int kfn_scoordnet_forward(kfn_handle* h, const uint8_t* images, int B, float* measure, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+  KFN_READY(h);
+  KFN_REQUIRE(images && measure && workspace && B > 0, "null/empty argument");
+  Arena ar(workspace, workspace_bytes);
+  return scoordnet_impl(h, images, B, measure, ar, (cudaStream_t)stream, false);
+}
+
+int kfn_oflow_feat_forward(kfn_handle* h, const uint8_t* images, int B, float* feat, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  KFN_READY(h);
+  KFN_REQUIRE(images && feat && workspace && B > 0, "null/empty argument");
+  Arena ar(workspace, workspace_bytes);
+  return tower_impl(h, images, B, feat, ar, (cudaStream_t)stream, false);
+}
+
+int kfn_diff_volume(const float* f_prev, const float* f_cur, int NP, int GH, int GW, void* diff, int out_bf16,
+                    void* stream) {
+  KFN_REQUIRE(f_prev && f_cur && diff && NP > 0 && GH > 0 && GW > 0, "null/empty argument");
+  return launch_diff_volume(f_prev, f_cur, NP, GH, GW, diff, out_bf16, (cudaStream_t)stream);
+}
+
+int kfn_oflownet_forward(kfn_handle* h, const float* f_prev, const float* f_cur, int NP, float* flow, float* sigma_w,
+                         float* logits, int32_t* argmax, void* workspace, int64_t workspace_bytes, void* stream) {
+  KFN_READY(h);
+  KFN_REQUIRE(f_prev && f_cur && flow && sigma_w && workspace && NP > 0, "null/empty argument");
+  Arena ar(workspace, workspace_bytes);
+  return oflownet_impl(h, f_prev, f_cur, NP, flow, sigma_w, logits, argmax, ar, (cudaStream_t)stream, false);
+}
+
+int kfn_kalman_scan(const float* measure, const float* flow, const float* sigma_w, const float* state_in,
+                    float* state_out, const float* transform, int S, int T, int GH, int GW, int first_index,
+                    int reinit_period, int nis_gate, float* out_map, float* temp, float* kf, float* nis,
+                    int32_t* taps, void* stream) {
+  KFN_REQUIRE(measure && flow && sigma_w && transform && out_map, "null argument");
+  return launch_kalman_scan(measure, flow, sigma_w, state_in, state_out, transform, S, T, GH, GW, first_index,
+                            reinit_period, nis_gate, out_map, temp, kf, nis, taps, (cudaStream_t)stream);
+}
+
+int kfn_flow_warp_kalman(const float* flow, const float* sigma_w, const float* last, const float* measure,
+                         const float* transform, int GH, int GW, float* temp, float* kf, float* nis, float* out_map,
+                         int32_t* taps, void* stream) {
+  KFN_REQUIRE(flow && sigma_w && last && measure && transform && out_map, "null argument");
+  return launch_kalman_scan(measure, flow, sigma_w, last, nullptr, transform, 1, 1, GH, GW, 1, 0, 0, out_map, temp, kf,
+                            nis, taps, (cudaStream_t)stream);
+}
+
+int64_t kfn_sequence_extra_bytes(kfn_handle* h, int S, int T) {
+  if (!h || S <= 0 || T <= 0) return KFN_ERR_ARG;
+  const int64_t F = (int64_t)S * T, P = (int64_t)h->GH * h->GW;
+  return F * P * (4 + 32 + 2 + 1) * 4 + 8 * 1024;
+}
+
+int kfn_eval_sequences(kfn_handle* h, const uint8_t* images, int S, int T, const float* transform, int reinit_period,
+                       int nis_gate, int frames_per_batch, int pairs_per_batch, float* out_map, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  KFN_READY(h);
+  KFN_REQUIRE(images && transform && out_map && workspace, "null argument");
+  KFN_REQUIRE(S > 0 && T > 0 && frames_per_batch > 0 && pairs_per_batch > 0, "empty problem");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t F = (int64_t)S * T, P = (int64_t)h->GH * h->GW;
+  Arena top(workspace, workspace_bytes);
+  float* measure = (float*)top.alloc(F * P * 4 * 4);
+  float* feat = (float*)top.alloc(F * P * 32 * 4);
+  float* flow = (float*)top.alloc(F * P * 2 * 4);
+  float* sigw = (float*)top.alloc(F * P * 4);
+  top.alloc(0);
+  if (top.overflow) { set_error("workspace too small for eval_sequences buffers"); return KFN_ERR_WORKSPACE; }
+  uint8_t* sub = reinterpret_cast<uint8_t*>(workspace) + top.off;
+  const int64_t sub_bytes = workspace_bytes - top.off;
+  const int64_t img_bytes = (int64_t)h->H * h->W * 3;
+  int rc;
+  // 1. measurement system + feature tower: frame-parallel over all S*T frames
+  for (int64_t f0 = 0; f0 < F; f0 += frames_per_batch) {
+    const int B = (int)((F - f0) < frames_per_batch ? (F - f0) : frames_per_batch);
+    { Arena a(sub, sub_bytes); if ((rc = scoordnet_impl(h, images + f0 * img_bytes, B, measure + f0 * P * 4, a, st, false))) return rc; }
+    { Arena a(sub, sub_bytes); if ((rc = tower_impl(h, images + f0 * img_bytes, B, feat + f0 * P * 32, a, st, false))) return rc; }
+  }
+  // 2. process system: pair (f-1, f) for every flat frame f >= 1.  Pairs that straddle two sequences are computed and
+  //    ignored (frame 0 of every sequence re-initialises the filter, eval.py:94-101).
+  for (int64_t f0 = 1; f0 < F; f0 += pairs_per_batch) {
+    const int NP = (int)((F - f0) < pairs_per_batch ? (F - f0) : pairs_per_batch);
+    Arena a(sub, sub_bytes);
+    if ((rc = oflownet_impl(h, feat + (f0 - 1) * P * 32, feat + f0 * P * 32, NP, flow + f0 * P * 2, sigw + f0 * P, nullptr,
+                            nullptr, a, st, false)))
+      return rc;
+  }
+  // 3. serial scan: warp + Kalman update, one CTA per sequence
+  const int period = reinit_period > 0 ? reinit_period : (1 << 30);
+  return launch_kalman_scan(measure, flow, sigw, nullptr, nullptr, transform, S, T, h->GH, h->GW, 0, period, nis_gate,
+                            out_map, nullptr, nullptr, nullptr, nullptr, st);
+}
+
+int kfn_conv_layer(kfn_handle* h, const char* op_key, const void* in, int N, int IH, int IW, int in_cs, void* out, int OH,
+                   int OW, int out_cs, int out_coff, int out_fp32, int epi, void* stream) {
+  KFN_READY(h);
+  KFN_REQUIRE(op_key && in && out && N > 0, "null/empty argument");
+  const std::string key(op_key);
+  Act a = act(const_cast<void*>(in), N, IH, IW, in_cs);
+  Act o = act(out, N, OH, OW, out_cs);
+  const size_t hash = key.find("#p");
+  if (hash != std::string::npos) {
+    const int ph = key[hash + 2] - '0';
+    KFN_REQUIRE(ph >= 0 && ph < 4 && OH == 2 * IH && OW == 2 * IW, "bad conv2d_transpose phase / shape");
+    return run_op(h, key, a, o, out_coff, IH, IW, 2, ph >> 1, ph & 1, epi, out_fp32 != 0, (cudaStream_t)stream);
+  }
+  return run_op(h, key, a, o, out_coff, OH, OW, 1, 0, 0, epi, out_fp32 != 0, (cudaStream_t)stream);
+}
+
+int64_t kfn_launch_count(kfn_handle* h, int reset) {
+  (void)h;
+  int64_t v = kfn::g_launches;
+  if (reset) kfn::g_launches = 0;
+  return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,325 @@
+// Memory-bound kernels of the KFNet path: input preprocessing, feature-difference volume,
+// softmax -> soft-argmax flow, and the serial warp + Kalman scan.  Compiled with --fmad=false so the
+// few flops here round exactly like the reference's separate fp32 TF ops (mul, add, div, sqrt).
+#include "common.cuh"
+
+namespace kfn {
+
+// ---------------------------------------------------------------------------------------------
+// (img - 128) * 0.00625  (cnn_wrapper/SCoordNet.py:34-37, KFNet/KFNet.py:317)
+__global__ void preprocess_f32_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = ((float)img[i] - 128.0f) * 0.00625f;
+}
+
+int launch_preprocess_f32(const uint8_t* img, float* out, int64_t n, cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  preprocess_f32_kernel<<<blocks, 256, 0, st>>>(img, out, n);
+  KFN_LAUNCH_OK();
+  return KFN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 SAME im2col of the raw image for the two Cin=3 first layers (SCoordNet conv1a, tower feat1):
+// out[b,y,x, (ky*3+kx)*3 + c] = img[b, y+ky-1, x+kx-1, c] - 128  (0 outside; k = 27..31 zero).
+// u8 - 128 is exact in bf16; the 0.00625 preprocess scale is folded into the packed weights.
+__global__ void im2col27_bf16_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H,
+                                     int W) {
+  int64_t total = (int64_t)B * H * W;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int x = (int)(i % W);
+  int y = (int)((i / W) % H);
+  const uint8_t* base = img + (i - (int64_t)y * W - x) * 3;   // start of image b
+  __align__(16) __nv_bfloat16 v[32];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    int yy = y + ky - 1;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      int xx = x + kx - 1;
+      bool inb = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+      const uint8_t* p = base + ((int64_t)yy * W + xx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        v[(ky * 3 + kx) * 3 + c] = __float2bfloat16(inb ? (float)p[c] - 128.0f : 0.0f);
+    }
+  }
+#pragma unroll
+  for (int k = 27; k < 32; ++k) v[k] = __float2bfloat16(0.0f);
+  uint4* dst = reinterpret_cast<uint4*>(out + i * 32);
+  const uint4* src = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dst[q] = src[q];
+}
+
+int launch_im2col27_bf16(const uint8_t* img, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st) {
+  int64_t total = (int64_t)B * H * W;
+  im2col27_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, out, B, H, W);
+  KFN_LAUNCH_OK();
+  return KFN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tf.nn.l2_normalize over 32 channels: x * rsqrt(max(sum x^2, 1e-12))  (KFNet/KFNet.py:340)
+__global__ void l2norm32_kernel(float* __restrict__ x, int64_t rows) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float4* p = reinterpret_cast<float4*>(x + r * 32);
+  float4 v[8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = p[i];
+    ss += v[i].x * v[i].x;
+    ss += v[i].y * v[i].y;
+    ss += v[i].z * v[i].z;
+    ss += v[i].w * v[i].w;
+  }
+  float inv = 1.0f / sqrtf(fmaxf(ss, 1e-12f));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i].x *= inv; v[i].y *= inv; v[i].z *= inv; v[i].w *= inv;
+    p[i] = v[i];
+  }
+}
+
+int launch_l2norm32(float* x, int64_t rows, cudaStream_t st) {
+  l2norm32_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(x, rows);
+  KFN_LAUNCH_OK();
+  return KFN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Feature-difference volume (KFNet.BuildCoordVolume, KFNet/KFNet.py:343-359, reshape :372):
+//   diff[n, p, i, j, c] = f_cur[n,p,c] - f_prev[n, p + (ox,oy), c],  (ox,oy) = (j-4, i-4), 0 outside.
+// One thread produces 16 bytes of output (4 fp32 or 8 bf16 channels); consecutive threads write
+// consecutive 16-byte words, so every warp store is one fully-coalesced 512-byte run.
+template <bool kBf16>
+__global__ void diff_volume_kernel(const float* __restrict__ f_prev, const float* __restrict__ f_cur,
+                                   void* __restrict__ out, int NP, int GH, int GW) {
+  constexpr int CH = kBf16 ? 8 : 4;          // channels per thread
+  constexpr int GROUPS = 32 / CH;            // threads per (pixel, offset)
+  const int P = GH * GW;
+  const int64_t total = (int64_t)NP * P * 64 * GROUPS;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; idx < total; idx += stride) {
+    int g = (int)(idx % GROUPS);
+    int k = (int)((idx / GROUPS) % 64);
+    int64_t np = idx / (GROUPS * 64);
+    int p = (int)(np % P);
+    int64_t n = np / P;
+    int y = p / GW, x = p - y * GW;
+    int yy = y + (k >> 3) - 4, xx = x + (k & 7) - 4;
+    bool inb = (yy >= 0) && (yy < GH) && (xx >= 0) && (xx < GW);
+    const float4* cur = reinterpret_cast<const float4*>(f_cur + (n * P + p) * 32 + g * CH);
+    const float4* prv = reinterpret_cast<const float4*>(f_prev + (n * P + (inb ? yy * GW + xx : 0)) * 32 + g * CH);
+    float4 a = __ldg(cur);
+    float4 b = inb ? __ldg(prv) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 d0 = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    if constexpr (!kBf16) {
+      reinterpret_cast<float4*>(out)[idx] = d0;
+    } else {
+      float4 a1 = __ldg(cur + 1);
+      float4 b1 = inb ? __ldg(prv + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(d0.x, d0.y);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(d0.z, d0.w);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(a1.x - b1.x, a1.y - b1.y);
+      __nv_bfloat162 h3 = __floats2bfloat162_rn(a1.z - b1.z, a1.w - b1.w);
+      uint4 o;
+      o.x = *reinterpret_cast<uint32_t*>(&h0);
+      o.y = *reinterpret_cast<uint32_t*>(&h1);
+      o.z = *reinterpret_cast<uint32_t*>(&h2);
+      o.w = *reinterpret_cast<uint32_t*>(&h3);
+      reinterpret_cast<uint4*>(out)[idx] = o;
+    }
+  }
+}
+
+int launch_diff_volume(const float* f_prev, const float* f_cur, int NP, int GH, int GW, void* diff, int out_bf16,
+                       cudaStream_t st) {
+  int64_t total = (int64_t)NP * GH * GW * 64 * (out_bf16 ? 4 : 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;   // grid-stride; multiple of the SM count
+  if (out_bf16)
+    diff_volume_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, diff, NP, GH, GW);
+  else
+    diff_volume_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, diff, NP, GH, GW);
+  KFN_LAUNCH_OK();
+  return KFN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// softmax over the 64 window logits -> soft-argmax flow (cnn_wrapper/OFlowNet.py:45-47,
+// KFNet/KFNet.py:381-385), argmax_k (diagnostic) and sigma_w = exp(u) * 1e-2 (OFlowNet.py:56).
+// One warp per label pixel: lane l owns logits k = 2l, 2l+1 (one coalesced 256-byte row per warp).
+__global__ void softmax_flow_kernel(const float* __restrict__ logits, const float* __restrict__ logsig,
+                                    int logsig_stride, int64_t rows, float* __restrict__ flow,
+                                    float* __restrict__ sigma_w, int32_t* __restrict__ argmax) {
+  const int lane = threadIdx.x & 31;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (; row < rows; row += wstride) {
+    float2 l = reinterpret_cast<const float2*>(logits + row * 64)[lane];
+    int k0 = 2 * lane;
+    float m = fmaxf(l.x, l.y);
+    int mi = (l.y > l.x) ? k0 + 1 : k0;          // lowest index wins ties (np.argmax)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float om = __shfl_xor_sync(0xffffffffu, m, o);
+      int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+      if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+    }
+    float e0 = expf(l.x - m), e1 = expf(l.y - m);
+    float s = e0 + e1;
+    // offsets[k] = (ox, oy) = (k%8 - 4, k/8 - 4)   (KFNet.py:348-350)
+    float ox0 = (float)((k0 & 7) - 4), oy0 = (float)((k0 >> 3) - 4);
+    float fx = e0 * ox0 + e1 * (ox0 + 1.0f);
+    float fy = (e0 + e1) * oy0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      fx += __shfl_xor_sync(0xffffffffu, fx, o);
+      fy += __shfl_xor_sync(0xffffffffu, fy, o);
+    }
+    if (lane == 0) {
+      flow[row * 2 + 0] = fx / s;
+      flow[row * 2 + 1] = fy / s;
+      sigma_w[row] = expf(logsig[row * logsig_stride]) * 1e-2f;
+      if (argmax) argmax[row] = mi;
+    }
+  }
+}
+
+int launch_softmax_flow(const float* logits, const float* logsig, int logsig_stride, int64_t rows, float* flow,
+                        float* sigma_w, int32_t* argmax, cudaStream_t st) {
+  int64_t blocks = (rows * 32 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  softmax_flow_kernel<<<(unsigned)blocks, 256, 0, st>>>(logits, logsig, logsig_stride, rows, flow, sigma_w, argmax);
+  KFN_LAUNCH_OK();
+  return KFN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Serial scan over frames: flow-guided bilinear warp of the filter state (tools/util.py:3-94 with
+// the clipped-neighbour weights of :56-59 and the add_n order of :90-93), process noise
+// (KFNet/KFNet.py:393-401), Kalman gain / posterior (KFNet.py:154-160), NIS (:164-184), rigid
+// transform (KFNet/util.py:31-37) and the state feedback / re-init of eval.py:87-104.
+// One CTA per sequence; the state (xyz, sigma) of all GH*GW pixels lives in shared memory
+// (double-buffered: the gather of frame t reads buffer t&1, the posterior goes to the other one).
+struct Xform { float m[16]; };
+
+__global__ void __launch_bounds__(1024, 1)
+kalman_scan_kernel(const float4* __restrict__ measure, const float2* __restrict__ flow, const float* __restrict__ sigma_w,
+                   const float4* __restrict__ state_in, float4* __restrict__ state_out, Xform X, int T, int GH, int GW,
+                   int first_index, int reinit_period, int nis_gate, float4* __restrict__ out_map,
+                   float4* __restrict__ temp, float4* __restrict__ kf, float* __restrict__ nis, int2* __restrict__ taps) {
+  extern __shared__ float4 s_state[];          // [2][P]
+  const int P = GH * GW;
+  const int s = blockIdx.x;
+  const int64_t seq = (int64_t)s * T * P;
+  float4* cur = s_state;
+  float4* nxt = s_state + P;
+  if (state_in) {
+    for (int p = threadIdx.x; p < P; p += blockDim.x) cur[p] = state_in[(int64_t)s * P + p];
+  }
+  __syncthreads();
+  const float xmax = (float)(GW - 1), ymax = (float)(GH - 1);
+  const float minvar = 1e-5f * 1e-5f;          // KFNet.py:71,396,398 (min_uncertainty^2)
+  for (int t = 0; t < T; ++t) {
+    const int64_t fr = seq + (int64_t)t * P;
+    const int idx = first_index + t;
+    const bool reinit = (reinit_period > 0) && (idx % reinit_period == 0);
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      const float4 z = measure[fr + p];        // (xyz, sigma_z)
+      float4 xm, xp;                           // prior (temp) and posterior (KF), w = sigma
+      float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+      int2 tp = make_int2(0, 0);
+      if (reinit) {
+        xm = z; xp = z;                        // eval.py:94-101
+      } else {
+        const float2 fl = flow[fr + p];
+        const int y = p / GW, x = p - y * GW;
+        const float cx = (float)x + fl.x, cy = (float)y + fl.y;          // KFNet.py:386
+        const float x0 = floorf(cx), y0 = floorf(cy);
+        const float x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+        const float x0s = fminf(fmaxf(x0, 0.f), xmax), x1s = fminf(fmaxf(x1, 0.f), xmax);
+        const float y0s = fminf(fmaxf(y0, 0.f), ymax), y1s = fminf(fmaxf(y1, 0.f), ymax);
+        const float wx0 = x1s - cx, wx1 = cx - x0s, wy0 = y1s - cy, wy1 = cy - y0s;
+        const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
+        const int ix0 = (int)x0s, ix1 = (int)x1s, iy0 = (int)y0s, iy1 = (int)y1s;
+        const float4 i00 = cur[iy0 * GW + ix0], i01 = cur[iy1 * GW + ix0];
+        const float4 i10 = cur[iy0 * GW + ix1], i11 = cur[iy1 * GW + ix1];
+        xm.x = ((w00 * i00.x + w01 * i01.x) + w10 * i10.x) + w11 * i11.x;
+        xm.y = ((w00 * i00.y + w01 * i01.y) + w10 * i10.y) + w11 * i11.y;
+        xm.z = ((w00 * i00.z + w01 * i01.z) + w10 * i10.z) + w11 * i11.z;
+        const float sl = ((w00 * i00.w + w01 * i01.w) + w10 * i10.w) + w11 * i11.w;
+        const float sw = sigma_w[fr + p];
+        const float last_var = fmaxf(sl * sl, minvar);
+        const float trans_var = fmaxf(sw * sw, minvar);
+        xm.w = sqrtf(trans_var + last_var);                               // temp_uncertainty
+        // BuildKFCoord (KFNet.py:154-160) -- squares temp_uncertainty again, like the reference
+        const float lv = xm.w * xm.w, mv = z.w * z.w;
+        const float K = lv / (lv + mv);
+        const float omk = fmaxf(1.0f - K, 0.0f);
+        xp.x = omk * xm.x + K * z.x;
+        xp.y = omk * xm.y + K * z.y;
+        xp.z = omk * xm.z + K * z.z;
+        xp.w = sqrtf(omk * lv);
+        // GetNIS (KFNet.py:164-184): inno_variance = square(sqrt(temp_var + measure_var))
+        const float iu = sqrtf(lv + mv);
+        const float iv = iu * iu;
+        const float d0 = z.x - xm.x, d1 = z.y - xm.y, d2 = z.z - xm.z;
+        n0 = (d0 * d0) / iv; n1 = (d1 * d1) / iv; n2 = (d2 * d2) / iv;
+        tp = make_int2((int)x0, (int)y0);
+      }
+      nxt[p] = xp;
+      // output map: (T * x+, 1/sigma+), NIS-gated to the transformed measurement if asked (eval.py:87-92,123)
+      float4 src = xp;
+      if (nis_gate && !reinit && ((n0 + n1) + n2 > 7.815f)) { src.x = z.x; src.y = z.y; src.z = z.z; }
+      float4 o;
+      o.x = ((X.m[0] * src.x + X.m[1] * src.y) + X.m[2] * src.z) + X.m[3];
+      o.y = ((X.m[4] * src.x + X.m[5] * src.y) + X.m[6] * src.z) + X.m[7];
+      o.z = ((X.m[8] * src.x + X.m[9] * src.y) + X.m[10] * src.z) + X.m[11];
+      o.w = 1.0f / xp.w;
+      out_map[fr + p] = o;
+      if (temp) temp[fr + p] = xm;
+      if (kf) kf[fr + p] = xp;
+      if (nis) { nis[(fr + p) * 3 + 0] = n0; nis[(fr + p) * 3 + 1] = n1; nis[(fr + p) * 3 + 2] = n2; }
+      if (taps) taps[fr + p] = tp;
+    }
+    __syncthreads();
+    float4* sw_ = cur; cur = nxt; nxt = sw_;
+  }
+  if (state_out) {
+    for (int p = threadIdx.x; p < P; p += blockDim.x) state_out[(int64_t)s * P + p] = cur[p];
+  }
+}
+
+int launch_kalman_scan(const float* measure, const float* flow, const float* sigma_w, const float* state_in,
+                       float* state_out, const float* T16_host, int S, int T, int GH, int GW, int first_index,
+                       int reinit_period, int nis_gate, float* out_map, float* temp, float* kf, float* nis,
+                       int32_t* taps, cudaStream_t st) {
+  KFN_REQUIRE(S > 0 && T > 0 && GH > 0 && GW > 0, "empty scan");
+  const size_t smem = (size_t)2 * GH * GW * sizeof(float4);
+  KFN_REQUIRE(smem <= 200 * 1024, "label grid too large for the shared-memory resident filter state");
+  Xform X;
+  for (int i = 0; i < 16; ++i) X.m[i] = T16_host[i];
+  static bool attr_set = false;
+  if (!attr_set) {
+    KFN_CUDA_OK(cudaFuncSetAttribute(kalman_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  kalman_scan_kernel<<<S, 1024, smem, st>>>(
+      reinterpret_cast<const float4*>(measure), reinterpret_cast<const float2*>(flow), sigma_w,
+      reinterpret_cast<const float4*>(state_in), reinterpret_cast<float4*>(state_out), X, T, GH, GW, first_index,
+      reinit_period, nis_gate, reinterpret_cast<float4*>(out_map), reinterpret_cast<float4*>(temp),
+      reinterpret_cast<float4*>(kf), nis, reinterpret_cast<int2*>(taps));
+  KFN_LAUNCH_OK();
+  return KFN_OK;
+}
+
+}  // namespace kfn

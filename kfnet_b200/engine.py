@@ -1,0 +1,164 @@
+"""Engine -- thin Python owner of one kfn_handle: weights in, device tensors through the C ABI.
+torch tensors are only the allocation / stream carrier; every kernel is in libkfnet_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synth import weight_shapes
+
+MODES = {"fp32": _lib.KFN_MODE_FP32, "bf16": _lib.KFN_MODE_BF16}
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, weights: dict, mode: str = "fp32", image_size=(480, 640), device: int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("kfnet_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.mode = mode
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.H, self.W = int(image_size[0]), int(image_size[1])
+        self.GH, self.GW = self.H // 8, self.W // 8
+        h = C.c_void_p()
+        _lib.check(self.lib.kfn_create(C.byref(h), self.device, MODES[mode], self.H, self.W))
+        self.h = h
+        self._ws = None
+        self.load_weights(weights)
+
+    # ---- weights (replaces tf.train.Saver restore by variable name, train.py:317-321) ----
+    def load_weights(self, weights: dict):
+        for name in weight_shapes():
+            if name not in weights:
+                raise KeyError(f"missing variable {name}")
+            a = np.ascontiguousarray(np.asarray(weights[name], dtype=np.float32))
+            dims = (C.c_int64 * a.ndim)(*a.shape)
+            _lib.check(self.lib.kfn_load_weight(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), dims, a.ndim))
+        _lib.check(self.lib.kfn_finalize_weights(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kfn_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers ----
+    def _dev(self):
+        return torch.device("cuda", self.device)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, nbytes: int):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self._dev())
+        return self._ws
+
+    def _chk_img(self, images):
+        assert images.is_cuda and images.dtype == torch.uint8 and images.is_contiguous()
+        assert tuple(images.shape[-3:]) == (self.H, self.W, 3), images.shape
+
+    def launch_count(self, reset=False) -> int:
+        return int(self.lib.kfn_launch_count(self.h, 1 if reset else 0))
+
+    # ---- SCoordNet: images u8 [B,H,W,3] -> measure fp32 [B,GH,GW,4] = (xyz, sigma_z) ----
+    def scoordnet(self, images):
+        self._chk_img(images)
+        B = images.shape[0]
+        out = torch.empty(B, self.GH, self.GW, 4, dtype=torch.float32, device=self._dev())
+        ws = self._workspace(self.lib.kfn_workspace_bytes(self.h, B, 0))
+        _lib.check(self.lib.kfn_scoordnet_forward(self.h, _ptr(images), B, _ptr(out), _ptr(ws), ws.numel(), self._stream()))
+        return out
+
+    # ---- feature tower: images -> l2-normalised feat fp32 [B,GH,GW,32] ----
+    def oflow_feat(self, images):
+        self._chk_img(images)
+        B = images.shape[0]
+        out = torch.empty(B, self.GH, self.GW, 32, dtype=torch.float32, device=self._dev())
+        ws = self._workspace(self.lib.kfn_workspace_bytes(self.h, B, 0))
+        _lib.check(self.lib.kfn_oflow_feat_forward(self.h, _ptr(images), B, _ptr(out), _ptr(ws), ws.numel(), self._stream()))
+        return out
+
+    def diff_volume(self, f_prev, f_cur, bf16=False):
+        NP, GH, GW, Cc = f_prev.shape
+        assert Cc == 32 and f_prev.dtype == torch.float32 and f_prev.is_contiguous() and f_cur.is_contiguous()
+        out = torch.empty(NP * GH * GW, 8, 8, 32, dtype=torch.bfloat16 if bf16 else torch.float32, device=f_prev.device)
+        _lib.check(self.lib.kfn_diff_volume(_ptr(f_prev), _ptr(f_cur), NP, GH, GW, _ptr(out), 1 if bf16 else 0, self._stream()))
+        return out
+
+    # ---- OFlowNet on NP pairs -> flow [NP,GH,GW,2], sigma_w [NP,GH,GW] (+ logits [NP*P,64], argmax) ----
+    def oflownet(self, f_prev, f_cur, want_logits=False, want_argmax=False):
+        assert f_prev.shape == f_cur.shape and f_prev.is_contiguous() and f_cur.is_contiguous()
+        NP = f_prev.shape[0]
+        dev = f_prev.device
+        flow = torch.empty(NP, self.GH, self.GW, 2, dtype=torch.float32, device=dev)
+        sig = torch.empty(NP, self.GH, self.GW, dtype=torch.float32, device=dev)
+        logits = torch.empty(NP * self.GH * self.GW, 64, dtype=torch.float32, device=dev) if want_logits else None
+        amax = torch.empty(NP, self.GH, self.GW, dtype=torch.int32, device=dev) if want_argmax else None
+        ws = self._workspace(self.lib.kfn_workspace_bytes(self.h, 0, NP))
+        _lib.check(self.lib.kfn_oflownet_forward(self.h, _ptr(f_prev), _ptr(f_cur), NP, _ptr(flow), _ptr(sig), _ptr(logits),
+                                                 _ptr(amax), _ptr(ws), ws.numel(), self._stream()))
+        return flow, sig, logits, amax
+
+    # ---- one packed layer by name (per-layer tests / roofline) ----
+    def conv_layer(self, key, x, out_hw, out_channels, out_coff=0, out=None, out_fp32=False, epi=0):
+        N, IH, IW, ics = x.shape
+        assert x.is_contiguous() and x.dtype == (torch.float32 if self.mode == "fp32" else torch.bfloat16)
+        odt = torch.float32 if (self.mode == "fp32" or out_fp32) else torch.bfloat16
+        if out is None:
+            out = torch.zeros(N, out_hw[0], out_hw[1], out_channels, dtype=odt, device=x.device)
+        _lib.check(self.lib.kfn_conv_layer(self.h, key.encode(), _ptr(x), N, IH, IW, ics, _ptr(out), out.shape[1], out.shape[2],
+                                           out.shape[3], out_coff, 1 if odt == torch.float32 else 0, epi, self._stream()))
+        return out
+
+    # ---- serial warp + Kalman scan over [S,T] ----
+    def kalman_scan(self, measure, flow, sigma_w, transform, state_in=None, first_index=0, reinit_period=500,
+                    nis_gate=False, diagnostics=False, want_state=False):
+        S, T, GH, GW, _ = measure.shape
+        dev = measure.device
+        for t in (measure, flow, sigma_w):
+            assert t.is_contiguous() and t.dtype == torch.float32
+        Tm = np.ascontiguousarray(np.asarray(transform, dtype=np.float32).reshape(16))
+        out = torch.empty(S, T, GH, GW, 4, dtype=torch.float32, device=dev)
+        temp = kf = nis = taps = state_out = None
+        if diagnostics:
+            temp = torch.empty_like(out); kf = torch.empty_like(out)
+            nis = torch.empty(S, T, GH, GW, 3, dtype=torch.float32, device=dev)
+            taps = torch.empty(S, T, GH, GW, 2, dtype=torch.int32, device=dev)
+        if want_state:
+            state_out = torch.empty(S, GH, GW, 4, dtype=torch.float32, device=dev)
+        _lib.check(self.lib.kfn_kalman_scan(_ptr(measure), _ptr(flow), _ptr(sigma_w), _ptr(state_in), _ptr(state_out),
+                                            Tm.ctypes.data_as(C.c_void_p), S, T, GH, GW, int(first_index), int(reinit_period),
+                                            1 if nis_gate else 0, _ptr(out), _ptr(temp), _ptr(kf), _ptr(nis), _ptr(taps),
+                                            self._stream()))
+        res = dict(out_map=out, temp=temp, kf=kf, nis=nis, taps=taps, state=state_out)
+        return res
+
+    # ---- whole batched eval path on device-resident sequences ----
+    def eval_sequences(self, images, transform, reinit_period=500, nis_gate=False, frames_per_batch=8, pairs_per_batch=4,
+                       out=None):
+        assert images.dim() == 5
+        self._chk_img(images)
+        S, T = images.shape[:2]
+        Tm = np.ascontiguousarray(np.asarray(transform, dtype=np.float32).reshape(16))
+        if out is None:
+            out = torch.empty(S, T, self.GH, self.GW, 4, dtype=torch.float32, device=images.device)
+        need = (self.lib.kfn_workspace_bytes(self.h, frames_per_batch, pairs_per_batch)
+                + self.lib.kfn_sequence_extra_bytes(self.h, S, T))
+        ws = self._workspace(need)
+        _lib.check(self.lib.kfn_eval_sequences(self.h, _ptr(images), S, T, Tm.ctypes.data_as(C.c_void_p), int(reinit_period),
+                                               1 if nis_gate else 0, int(frames_per_batch), int(pairs_per_batch), _ptr(out),
+                                               _ptr(ws), ws.numel(), self._stream()))
+        return out

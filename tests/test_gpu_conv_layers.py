@@ -1,0 +1,112 @@
+"""GPU parity of single layers through kfn_conv_layer, both compute modes, vs a plain PyTorch fp32 conv of the
+same op (oracle ops on the GPU).  BF16 mode: inputs/weights are bf16-representable and the accumulator is fp32,
+so with fp32 output the tcgen05 path must agree with the fp32 reference to accumulation-order noise."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kfnet_oracle as O
+from tests.golden import cases
+from tests.util import assert_close_rms, gpu_setup
+
+pytestmark = pytest.mark.gpu
+
+# (key, kind, k, cin, cout, stride, relu, N, IH, IW)  -- shapes chosen to exercise every tile-box / swizzle / tap variant
+LAYERS = [
+    ("ScoreNet/conv1b", "conv", 3, 64, 64, 1, True, 2, 16, 32),       # KC64 BN64, box 16x8x1... s1 halo via TMA OOB
+    ("ScoreNet/conv2a", "conv", 3, 64, 256, 2, True, 2, 16, 32),      # stride 2 parity view, BN256
+    ("ScoreNet/conv3a", "conv", 3, 256, 512, 2, True, 3, 8, 16),      # two N tiles, odd batch (OOB in n)
+    ("ScoreNet/conv4b", "conv", 3, 1024, 1024, 1, True, 1, 8, 12),    # K = 9216: deep pipeline, 4 N tiles, W=12 -> bw=4
+    ("ScoreNet/conv7", "conv", 1, 256, 128, 1, True, 2, 8, 12),
+    ("ScoreNet/prediction", "conv", 1, 128, 4, 1, False, 2, 8, 12),   # Cout 4 padded to 16
+    ("Temporal/feat2", "conv", 3, 16, 32, 2, True, 2, 16, 32),        # KC16 (32B swizzle)
+    ("Temporal/feat3", "conv", 3, 32, 32, 1, True, 2, 8, 16),         # KC32 (64B swizzle)
+    ("Temporal/feat6", "conv", 3, 64, 128, 2, True, 2, 16, 24),
+    ("Temporal/conv0", "conv", 3, 32, 32, 1, True, 50, 8, 8),         # U-Net 8x8 windows, box 8x8x2
+    ("Temporal/conv1a", "conv", 3, 32, 32, 2, True, 50, 8, 8),
+    ("Temporal/conv2a", "conv", 3, 32, 64, 2, True, 70, 4, 4),
+    ("Temporal/conv2b", "conv", 3, 64, 64, 1, True, 70, 2, 2),
+    ("Temporal/conv3a", "conv", 3, 64, 128, 2, True, 300, 2, 2),      # -> 1x1, pruned taps
+    ("Temporal/conv3b", "conv", 3, 128, 128, 1, True, 300, 1, 1),     # centre tap only
+    ("Temporal/conv6", "conv", 3, 48, 16, 1, True, 50, 8, 8),         # Cin 48 -> 3 chunks of 16
+    ("Temporal/prediction", "conv", 3, 16, 1, 1, False, 50, 8, 8),
+    ("Temporal/fc1", "dense", 1, 128, 64, 1, True, 300, 1, 1),
+    ("Temporal/uncertainty", "dense", 1, 32, 1, 1, False, 300, 1, 1),
+]
+DECONVS = [("Temporal/upconv2", 128, 64, 300, 1), ("Temporal/upconv1", 64, 32, 70, 2), ("Temporal/upconv0", 32, 16, 50, 4)]
+
+
+@pytest.fixture(scope="module")
+def engines(weights):
+    gpu_setup()
+    from kfnet_b200.engine import Engine
+    return {m: Engine(weights, mode=m, image_size=cases.SMALL_HW) for m in ("fp32", "bf16")}
+
+
+def _ref_layer(weights, key, kind, x, stride, relu, round_w):
+    w = torch.tensor(weights[key + "/kernel"]).cuda()
+    b = torch.tensor(weights[key + "/bias"]).cuda()
+    if round_w:
+        w = w.to(torch.bfloat16).float()
+    if kind == "dense":
+        w = w.reshape(1, 1, *w.shape)
+    return O.conv2d_same(x, w, b, stride, relu)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("spec", LAYERS, ids=[s[0] for s in LAYERS])
+def test_conv_layer(engines, weights, mode, spec):
+    key, kind, k, cin, cout, stride, relu, N, IH, IW = spec
+    g = torch.Generator().manual_seed(abs(hash(key)) % 1000)
+    x = torch.randn(N, IH, IW, cin, generator=g).cuda()
+    eng = engines[mode]
+    OH, OW = IH // stride, IW // stride
+    if mode == "bf16":
+        xb = x.to(torch.bfloat16)
+        ref = _ref_layer(weights, key, kind, xb.float(), stride, relu, True)
+        got = eng.conv_layer(key, xb.contiguous(), (OH, OW), cout, out_fp32=True)
+        assert_close_rms(got, ref, 2e-4, key + " bf16 operands / fp32 out")
+        got16 = eng.conv_layer(key, xb.contiguous(), (OH, OW), cout, out_fp32=False)
+        assert_close_rms(got16.float(), ref, 1e-2, key + " bf16 out")
+    else:
+        ref = _ref_layer(weights, key, kind, x, stride, relu, False)
+        got = eng.conv_layer(key, x.contiguous(), (OH, OW), cout)
+        assert_close_rms(got, ref, 2e-5, key + " fp32")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("spec", DECONVS, ids=[s[0] for s in DECONVS])
+def test_deconv_phases_and_concat_offset(engines, weights, mode, spec):
+    """conv2d_transpose = 4 sub-pixel phases, written into channels [0,Cout) of a wider concat buffer."""
+    key, cin, cout, N, n = spec
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, n, n, cin, generator=g).cuda()
+    eng = engines[mode]
+    w = torch.tensor(weights[key + "/kernel"]).cuda()
+    b = torch.tensor(weights[key + "/bias"]).cuda()
+    ctot = cout + 32
+    if mode == "bf16":
+        x = x.to(torch.bfloat16)
+        ref = O.conv2d_transpose_same(x.float(), w.to(torch.bfloat16).float(), b, True)
+    else:
+        ref = O.conv2d_transpose_same(x, w, b, True)
+    out = torch.full((N, 2 * n, 2 * n, ctot), 7.0, dtype=x.dtype, device="cuda")
+    for ph in range(4):
+        eng.conv_layer(f"{key}#p{ph}", x.contiguous(), (2 * n, 2 * n), ctot, out_coff=0, out=out)
+    assert_close_rms(out[..., :cout].float(), ref, 1e-2 if mode == "bf16" else 2e-5, key)
+    assert bool((out[..., cout:] == 7.0).all()), "channels outside [0,Cout) must be untouched"
+
+
+def test_first_layer_im2col_weights(engines, weights):
+    """BF16 mode runs the Cin=3 layers as a 1-tap GEMM over the 32-wide im2col row with 0.00625 folded into W."""
+    g = torch.Generator().manual_seed(1)
+    img = torch.randint(0, 256, (2, 16, 24, 3), generator=g).float().cuda()
+    x = (img - 128.0).permute(0, 3, 1, 2)
+    cols = torch.nn.functional.unfold(x, 3, padding=1).reshape(2, 3, 9, 16, 24)          # [n, c, tap, h, w]
+    cols = cols.permute(0, 3, 4, 2, 1).reshape(2, 16, 24, 27)
+    cols = torch.cat([cols, torch.zeros(2, 16, 24, 5, device="cuda")], -1).to(torch.bfloat16).contiguous()
+    for key, cout in (("ScoreNet/conv1a", 64), ("Temporal/feat1", 16)):
+        w = (torch.tensor(weights[key + "/kernel"]).cuda() * 0.00625).to(torch.bfloat16).float() / 0.00625
+        ref = O.conv2d_same(O.preprocess(img), w, torch.tensor(weights[key + "/bias"]).cuda(), 1, True)
+        got = engines["bf16"].conv_layer(key, cols, (16, 24), cout, out_fp32=True)
+        assert_close_rms(got, ref, 5e-4, key)

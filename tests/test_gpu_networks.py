@@ -1,0 +1,135 @@
+"""GPU parity of the network stages and the whole eval path vs the CPU oracle and the committed golden
+vectors (reference source on the TF1 shim).  fp32 mode: 1e-4 on coordinate maps and log-sigma (north_star
+tolerance); bf16 mode: error vs the fp64 oracle reported next to a documented looser bound."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kfnet_oracle as O
+from tests.golden import cases
+from tests.util import assert_close_rms, gpu_setup, rms_rel_err
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 0.12      # bf16 activations through 12 (+7+14) layers; measured values are printed by the tests
+
+
+@pytest.fixture(scope="module")
+def small(weights):
+    gpu_setup()
+    from kfnet_b200.engine import Engine
+    return {m: Engine(weights, mode=m, image_size=cases.SMALL_HW) for m in ("fp32", "bf16")}
+
+
+@pytest.fixture(scope="module")
+def full(weights):
+    gpu_setup()
+    from kfnet_b200.engine import Engine
+    return {m: Engine(weights, mode=m, image_size=(480, 640)) for m in ("fp32", "bf16")}
+
+
+def _u8(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(torch.uint8).cuda().contiguous()
+
+
+def test_scoordnet_and_tower_small_vs_golden(small, golden):
+    imgs = cases.small_images(2, seed=5)
+    m = small["fp32"].scoordnet(_u8(imgs)).cpu()
+    f = small["fp32"].oflow_feat(_u8(imgs)).cpu()
+    assert_close_rms(m[1:2, ..., :3], golden["small_rec_measure_coord"], 1e-4, "measure coord")
+    assert_close_rms(torch.log(m[1:2, ..., 3:4]), np.log(golden["small_rec_measure_unc"]), 1e-4, "log sigma_z")
+    assert_close_rms(f, golden["small_rec_feat"], 1e-4, "tower features")
+    mb = small["bf16"].scoordnet(_u8(imgs)).cpu()
+    fb = small["bf16"].oflow_feat(_u8(imgs)).cpu()
+    print("bf16 small: coord err", assert_close_rms(mb[1:2, ..., :3], golden["small_rec_measure_coord"], BF16_TOL, "bf16 coord"),
+          "feat err", assert_close_rms(fb, golden["small_rec_feat"], BF16_TOL, "bf16 feat"))
+
+
+def test_recursive_step_full_480x640_vs_golden(full, golden):
+    """One GetKFCoordRecursive step at full size: every fetched tensor of eval.py:78-83 vs the golden fixture."""
+    from kfnet_b200 import KFNet, KFNetDataSpec
+    imgs = cases.full_images()
+    lc, lu = (torch.tensor(s, dtype=torch.float32).cuda() for s in cases.full_state())
+    for mode, tol in (("fp32", 1e-4), ("bf16", BF16_TOL)):
+        net = KFNet(_u8(imgs), KFNetDataSpec(batch_size=2), engine=full[mode])
+        mc, mu = net.GetMeasureCoord2()
+        tc, tu, kc, ku = net.GetKFCoordRecursive(lc, lu)
+        nis = net.GetNIS(mc, mu, tc, tu)
+        errs = dict(
+            feat=rms_rel_err(net.temp_feat_maps, golden["full_rec_feat"]),
+            measure_coord=rms_rel_err(mc, golden["full_rec_measure_coord"]),
+            log_measure_unc=rms_rel_err(torch.log(mu), np.log(golden["full_rec_measure_unc"])),
+            temp_coord=rms_rel_err(tc, golden["full_rec_temp_coord"]),
+            log_temp_unc=rms_rel_err(torch.log(tu), np.log(golden["full_rec_temp_unc"])),
+            kf_coord=rms_rel_err(kc, golden["full_rec_kf_coord"]),
+            log_kf_unc=rms_rel_err(torch.log(ku), np.log(golden["full_rec_kf_unc"])),
+        )
+        print(mode, {k: f"{v:.2e}" for k, v in errs.items()})
+        for k, v in errs.items():
+            assert v <= tol, f"{mode} {k}: {v:.3e} > {tol}"
+        if mode == "fp32":
+            assert_close_rms(nis, golden["full_rec_nis"], 2e-3, "nis")
+
+
+def test_batch4_unrolled_equals_recursive_and_golden(small, golden):
+    """GetKFCoordBatch (KFNet.py:102-146) == scan over the same 4 frames == golden."""
+    from kfnet_b200 import KFNet, KFNetDataSpec
+    imgs = cases.small_images(4, seed=7)
+    net = KFNet(_u8(imgs), KFNetDataSpec(batch_size=4, image_size=cases.SMALL_HW), engine=small["fp32"])
+    tc, tu, kc, ku = net.GetKFCoordBatch()
+    assert_close_rms(tc, golden["small_b4_temp_coord"], 1e-4, "temp_coord")
+    assert_close_rms(kc, golden["small_b4_kf_coord"], 1e-4, "kf_coord")
+    assert_close_rms(torch.log(ku), np.log(golden["small_b4_kf_unc"]), 1e-4, "log kf_unc")
+    assert_close_rms(torch.log(tu), np.log(golden["small_b4_temp_unc"]), 1e-4, "log temp_unc")
+
+
+def test_eval_sequences_small_vs_oracle(small, weights):
+    """Whole batched path (S=2 sequences x T=6 frames, ragged batches, re-init every 4) vs the fp64 oracle loop."""
+    S, T = 2, 6
+    Tm = cases.transform().astype(np.float32)
+    seqs = [cases.small_images(T, seed=30 + s) for s in range(S)]
+    ref = torch.stack([torch.stack([r.out_map for r in O.eval_sequence(q, weights, Tm, seq_len=4, dtype=torch.float64)])
+                       for q in seqs]).float()
+    dev = _u8(np.stack(seqs))
+    out = small["fp32"].eval_sequences(dev, Tm, reinit_period=4, frames_per_batch=5, pairs_per_batch=3).cpu()
+    e = assert_close_rms(out[..., :3], ref[..., :3], 1e-4, "eval out coords")
+    e2 = assert_close_rms(torch.log(out[..., 3]), torch.log(ref[..., 3]), 1e-4, "eval out log confidence")
+    outb = small["bf16"].eval_sequences(dev, Tm, reinit_period=4, frames_per_batch=4, pairs_per_batch=2).cpu()
+    eb = assert_close_rms(outb[..., :3], ref[..., :3], 0.25, "bf16 eval out coords")
+    print(f"eval_sequences small: fp32 err {e:.2e}/{e2:.2e}, bf16 err {eb:.2e}")
+    # determinism / batch-size independence: different batching gives bit-identical results
+    out2 = small["fp32"].eval_sequences(dev, Tm, reinit_period=4, frames_per_batch=12, pairs_per_batch=11).cpu()
+    assert torch.equal(out, out2)
+
+
+def test_scoordnet_batch8_full_vs_oracle(full, weights):
+    """BASELINE config 2: SCoordNet, batch 8 synthetic 480x640, vs the fp32/fp64 oracle on two of the frames."""
+    from kfnet_b200 import synth
+    imgs = synth.make_sequence(8, seed=1)
+    dev = _u8(imgs)
+    m32 = full["fp32"].scoordnet(dev).cpu()
+    mbf = full["bf16"].scoordnet(dev).cpu()
+    for t in (0, 5):
+        c64, u64 = O.scoordnet(imgs[t:t + 1].astype(np.float32), weights, torch.float64)
+        c32, u32 = O.scoordnet(imgs[t:t + 1].astype(np.float32), weights, torch.float32)
+        e_or = rms_rel_err(c32, c64)
+        e32 = assert_close_rms(m32[t:t + 1, ..., :3], c64, 1e-4, "fp32 mode coord")
+        assert_close_rms(torch.log(m32[t:t + 1, ..., 3:4]), torch.log(u64), 1e-4, "fp32 mode log sigma")
+        ebf = assert_close_rms(mbf[t:t + 1, ..., :3], c64, BF16_TOL, "bf16 mode coord")
+        print(f"frame {t}: oracle fp32 self-error {e_or:.2e}; fp32 mode {e32:.2e}; bf16 mode {ebf:.2e}")
+
+
+def test_bf16_flow_indices_vs_fp32_mode(full):
+    """argmax / tap indices of the bf16 path vs the fp32 path on a real pair, excluding near-ties."""
+    from kfnet_b200 import synth
+    dev = _u8(synth.make_sequence(2, seed=1))
+    f = full["fp32"].oflow_feat(dev)
+    fl32, sg32, lg32, am32 = full["fp32"].oflownet(f[:1].contiguous(), f[1:].contiguous(), True, True)
+    fb = full["bf16"].oflow_feat(dev)
+    flb, sgb, lgb, amb = full["bf16"].oflownet(fb[:1].contiguous(), fb[1:].contiguous(), True, True)
+    top2 = lg32.topk(2, -1).values
+    margin = (top2[:, 0] - top2[:, 1])
+    decided = margin > 0.25 * lg32.std()
+    agree = (am32.reshape(-1)[decided] == amb.reshape(-1)[decided]).float().mean().item()
+    print(f"bf16 vs fp32: flow err {rms_rel_err(flb, fl32):.2e}, log-sigma_w err {rms_rel_err(sgb.log(), sg32.log()):.2e}, "
+          f"argmax agreement off near-ties {agree:.4f} ({int(decided.sum())} of {decided.numel()} px decided)")
+    assert agree > 0.97

@@ -1,0 +1,21 @@
+import numpy as np
+import torch
+
+
+def rms_rel_err(a, b):
+    """max |a-b| / max(|b|, rms(b)) -- the tolerance form of SURVEY 8(c) (warped borders are legitimately ~0)."""
+    a = torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).double().cpu()
+    b = torch.as_tensor(np.asarray(b) if not isinstance(b, torch.Tensor) else b).double().cpu()
+    s = b.pow(2).mean().sqrt().clamp_min(1e-30)
+    return float(((a - b).abs() / torch.maximum(b.abs(), s)).max())
+
+
+def assert_close_rms(a, b, tol, what=""):
+    e = rms_rel_err(a, b)
+    assert e <= tol, f"{what}: rms-relative error {e:.3e} > {tol:.1e}"
+    return e
+
+
+def gpu_setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
