@@ -328,6 +328,10 @@ def eval_sequence(images, weights, transform, seq_len=500, nis_gate=False, dtype
             z, zunc, fa, fb = zc[i], zu[i], feats[prev], feats[i]
         if i % seq_len == 0:
             # eval.py:94-101: state and outputs := measurement (KF work of this iteration is discarded)
+            if faithful_redundancy:   # the reference still executes the whole graph in this sess.run (timing fidelity)
+                lc0 = last_coord if last_coord is not None else torch.zeros_like(z)
+                lu0 = last_unc if last_unc is not None else torch.ones_like(zunc)
+                build_oflownet(fa, fb, lc0, lu0, weights, dtype)
             fo = FrameOut(z, zunc, z, zunc, z, zunc, torch.zeros_like(z),
                           torch.cat([apply_transform(z, Tm), 1.0 / zunc], -1)[0])
             last_coord, last_unc = z, zunc

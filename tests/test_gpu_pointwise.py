@@ -83,8 +83,11 @@ def test_kalman_scan_matches_oracle_sequence(eng):
 def test_kalman_nis_gate_and_single_step(eng):
     GH, GW = 8, 12
     g = torch.Generator().manual_seed(9)
-    last = torch.randn(1, GH, GW, 4, generator=g); last[..., 3] = torch.rand(1, GH, GW, generator=g) * 0.05 + 0.01
-    meas = torch.randn(1, 1, GH, GW, 4, generator=g) * 3; meas[..., 3] = 0.05
+    last = torch.ones(1, GH, GW, 4) * torch.tensor([0.5, -1.0, 2.0, 0.05])      # constant state: the warp returns it (off-border)
+    noise = torch.randn(1, 1, GH, GW, 3, generator=g)
+    noise[..., : GW // 2, :] *= 0.01                                             # left half: consistent measurement
+    noise[..., GW // 2:, :] *= 3.0                                               # right half: outliers -> gated
+    meas = torch.cat([last[None, ..., :3] + noise, torch.full((1, 1, GH, GW, 1), 0.05)], -1)
     flow = torch.rand(1, 1, GH, GW, 2, generator=g) * 2 - 1
     sw = torch.full((1, 1, GH, GW), 0.01)
     Tm = cases.transform().astype(np.float32)

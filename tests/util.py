@@ -19,3 +19,13 @@ def assert_close_rms(a, b, tol, what=""):
 def gpu_setup():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def rel_err_quantile(a, b, q):
+    """q-quantile of |a-b| / max(|b|, rms(b)): robust form for bf16-mode WARPED maps, where a sample point crossing the
+    sampler's x = W-1 / y = H-1 edge (tools/util.py:56-59 weights) legitimately flips single pixels between ~0 and a value."""
+    a = torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).double().cpu()
+    b = torch.as_tensor(np.asarray(b) if not isinstance(b, torch.Tensor) else b).double().cpu()
+    s = b.pow(2).mean().sqrt().clamp_min(1e-30)
+    e = ((a - b).abs() / torch.maximum(b.abs(), s)).reshape(-1)
+    return float(torch.quantile(e, q))

@@ -8,7 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 rc=0
 for f in "$@"; do
   name=$(basename "$f" .py)
-  timeout 900 python -m pytest "$f" -q -x -s -m gpu > "gpurun_out/$name.log" 2>&1
+  timeout 900 python -m pytest "$f" -q -s -m gpu --tb=short > "gpurun_out/$name.log" 2>&1
   r=$?
   echo "== $f -> exit $r"; tail -n 30 "gpurun_out/$name.log"
   [ $r -ne 0 ] && rc=$r
