@@ -149,6 +149,7 @@ def run_ours(args):
         dist.barrier()
     from kfnet_b200 import synth
     from kfnet_b200.engine import Engine
+    from kfnet_b200.shard import gather_outputs
 
     T, H, W = args.frames, 480, 640
     weights = synth.make_weights(0)
@@ -162,14 +163,13 @@ def run_ours(args):
         host_imgs[0, t0:t0 + n] = torch.from_numpy(np.roll(base[:n], shift=t0 // base.shape[0], axis=2))
     dev_imgs = host_imgs.cuda(non_blocking=False)
     out = torch.empty(1, T, eng.GH, eng.GW, 4, dtype=torch.float32, device="cuda")
-    gathered = torch.empty(world, T, eng.GH, eng.GW, 4, dtype=torch.float32, device="cuda") if world > 1 else None
     host_out = torch.empty((1, T, eng.GH, eng.GW, 4), dtype=torch.float32).pin_memory()
     fpb, ppb = args.frames_per_batch, args.pairs_per_batch
 
     def step_resident():
         eng.eval_sequences(dev_imgs, Tm, reinit_period=500, frames_per_batch=fpb, pairs_per_batch=ppb, out=out)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out[0])
+            gather_outputs(out, world)          # the path's single collective: all_gather of the per-rank output maps
 
     stage = torch.empty_like(dev_imgs)
 
@@ -178,7 +178,7 @@ def run_ours(args):
         eng.eval_sequences(stage, Tm, reinit_period=500, frames_per_batch=fpb, pairs_per_batch=ppb, out=out)
         host_out.copy_(out, non_blocking=True)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out[0])
+            gather_outputs(out, world)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
