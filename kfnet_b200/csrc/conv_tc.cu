@@ -16,6 +16,7 @@
 // warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -46,6 +47,14 @@ struct __align__(8) TcParams {
   int OH, OW, out_cs, out_coff, Cout, omul, oaddy, oaddx, relu, epi, out_bf16;
   void* out;
   const float* bias;            // [CoutP] zero padded
+  // halo mode (stride-1 3x3 layers whose weights fit in smem): the (8 x bh x bn) pixel tile's haloed input block
+  // is loaded ONCE per channel chunk (rows ordered [y][n][x], 10 pixels per image row) and every tap is an MMA
+  // whose A descriptor starts at a shifted row with a 10-row group pitch (tools/umma_probe.cu: the 128B swizzle
+  // is a function of absolute smem address bits, so shifted starts / non-canonical SBO read the right rows).
+  int halo, lbn, row_bytes;
+  uint32_t desc_hi_halo;        // A descriptor upper word with SBO = 10 rows
+  uint32_t w_tile_bytes, w_bytes_total;
+  uint32_t tap_off16[9];        // halo: ((1+dy) * 10*bn + (1+dx)) * row_bytes / 16 per tap
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -95,6 +104,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// One k-block: KSTEPS MMAs (UMMA_K = 16 bf16 = 32 bytes = +2 in descriptor units); only the first may overwrite D.
+template <int KSTEPS>
+__device__ __forceinline__ void umma_kblock(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum_first) {
+  umma_bf16(tmem_d, adesc, bdesc, idesc, accum_first);
+#pragma unroll
+  for (int k = 1; k < KSTEPS; ++k) umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -118,6 +134,78 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// ------------------------------------------------------------------------------------------ MMA issuer roles
+// Descriptors are 64-bit values advanced with adds of precomputed constants (start address field is in 16-byte
+// units and never overflows its 14 bits for addresses < 256 KB), so one issued MMA costs a couple of uniform
+// instructions instead of a descriptor rebuild.
+template <int KSTEPS>
+__device__ __forceinline__ void mma_role(const TcParams& p, uint32_t smem_base, uint32_t tmem_base, int total_tiles, int kblocks,
+                                         uint64_t* s_full, uint64_t* s_empty, uint64_t* s_tfull, uint64_t* s_tempty) {
+  const uint64_t desc_fixed = ((uint64_t)p.desc_hi << 32) | (1ull << 16);
+  const uint64_t stage16 = (uint64_t)(p.stage_bytes >> 4);
+  const uint64_t a0 = desc_fixed | (uint64_t)(smem_base >> 4);
+  const uint64_t b_off = (uint64_t)(p.a_bytes >> 4);
+  int s = 0, j = 0;
+  uint32_t ph = 0;
+  uint64_t adesc = a0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+    const int a = j & 1;
+    const uint32_t aph = (uint32_t)(j >> 1) & 1u;
+    mbar_wait(smem_u32(&s_tempty[a]), aph ^ 1u);
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base + (uint32_t)a * 256u;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      mbar_wait(smem_u32(&s_full[s]), ph);
+      tc_fence_after();
+      umma_kblock<KSTEPS>(tmem_d, adesc, adesc + b_off, p.idesc, kb ? 1u : 0u);
+      umma_commit(smem_u32(&s_empty[s]));       // frees the smem stage once these MMAs retire
+      adesc += stage16;
+      if (++s == p.stages) { s = 0; ph ^= 1u; adesc = a0; }
+    }
+    umma_commit(smem_u32(&s_tfull[a]));          // accumulator ready for the epilogue
+  }
+}
+
+template <int KSTEPS>
+__device__ __forceinline__ void mma_role_halo(const TcParams& p, uint32_t smem_base, uint32_t tmem_base, int total_tiles,
+                                              uint64_t* s_full, uint64_t* s_empty, uint64_t* s_tfull, uint64_t* s_tempty,
+                                              uint64_t* s_wbar) {
+  mbar_wait(smem_u32(s_wbar), 0);               // resident weights have landed
+  const uint64_t a_fixed = ((uint64_t)p.desc_hi_halo << 32) | (1ull << 16);
+  const uint64_t b_fixed = ((uint64_t)p.desc_hi << 32) | (1ull << 16);
+  const uint64_t stage16 = (uint64_t)(p.stage_bytes >> 4);
+  const uint64_t a0 = a_fixed | (uint64_t)((smem_base + p.w_bytes_total) >> 4);
+  const uint64_t b0 = b_fixed | (uint64_t)(smem_base >> 4);
+  const uint64_t wtile16 = (uint64_t)(p.w_tile_bytes >> 4);
+  const uint64_t wtap16 = wtile16 * (uint64_t)p.kchunks;
+  int s = 0, j = 0;
+  uint32_t ph = 0;
+  uint64_t adesc = a0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+    const int a = j & 1;
+    const uint32_t aph = (uint32_t)(j >> 1) & 1u;
+    mbar_wait(smem_u32(&s_tempty[a]), aph ^ 1u);
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base + (uint32_t)a * 256u;
+    uint64_t bchunk = b0;
+    for (int kc = 0; kc < p.kchunks; ++kc) {
+      mbar_wait(smem_u32(&s_full[s]), ph);
+      tc_fence_after();
+      uint64_t bdesc = bchunk;
+      umma_kblock<KSTEPS>(tmem_d, adesc + (uint64_t)p.tap_off16[0], bdesc, p.idesc, kc ? 1u : 0u);
+      for (int tap = 1; tap < p.ntaps; ++tap) {
+        bdesc += wtap16;
+        umma_kblock<KSTEPS>(tmem_d, adesc + (uint64_t)p.tap_off16[tap], bdesc, p.idesc, 1u);
+      }
+      umma_commit(smem_u32(&s_empty[s]));
+      bchunk += wtile16;
+      adesc += stage16;
+      if (++s == p.stages) { s = 0; ph ^= 1u; adesc = a0; }
+    }
+    umma_commit(smem_u32(&s_tfull[a]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -127,6 +215,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t s_tfull[2];
   __shared__ __align__(8) uint64_t s_tempty[2];
   __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(8) uint64_t s_wbar;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,6 +230,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(smem_u32(&s_tfull[a]), 1);
       mbar_init(smem_u32(&s_tempty[a]), 4);
     }
+    mbar_init(smem_u32(&s_wbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -165,7 +255,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================================================================== TMA producer (one lane)
-    if (lane == 0) {
+    if (lane == 0 && p.halo) {
+      // resident weights: every (tap, chunk) tile once, one barrier
+      const uint32_t wbar = smem_u32(&s_wbar);
+      mbar_expect_tx(wbar, (uint32_t)(p.ntaps * p.kchunks) * p.b_bytes);
+      for (int tap = 0; tap < p.ntaps; ++tap)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_3d(smem_base + (uint32_t)(tap * p.kchunks + kc) * p.w_tile_bytes, &tmB, wbar, kc * p.KC, 0, tap);
+      const uint32_t stage0 = smem_base + p.w_bytes_total;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt = tile;
+        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int tn = mt / p.tiles_h;
+        const int w0 = tw << 3, h0 = th << p.lbh, n0 = tn << p.lbn;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);
+          const uint32_t full = smem_u32(&s_full[s]);
+          mbar_expect_tx(full, p.a_bytes);
+          tma_load_5d(stage0 + (uint32_t)s * p.stage_bytes, &tmA, full, kc * p.KC, w0 - 1, n0, h0 - 1, 0);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    } else if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -195,40 +309,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (one lane)
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      int j = 0;
-      const uint64_t desc_hi = (uint64_t)p.desc_hi << 32;
-      const int ksteps = p.KC >> 4;    // UMMA_K = 16 bf16 = 32 bytes
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
-        const int a = j & 1;
-        const uint32_t aph = (uint32_t)(j >> 1) & 1u;
-        mbar_wait(smem_u32(&s_tempty[a]), aph ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)a * 256u;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(smem_u32(&s_full[s]), ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + (uint32_t)s * p.stage_bytes;
-          const uint32_t b_addr = a_addr + p.a_bytes;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + k * 32) >> 4) & 0x3FFFu) | (1ull << 16);
-            const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFFu) | (1ull << 16);
-            umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb | k) ? 1u : 0u);
-          }
-          umma_commit(smem_u32(&s_empty[s]));       // frees the smem stage once these MMAs retire
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
-        }
-        umma_commit(smem_u32(&s_tfull[a]));          // accumulator ready for the epilogue
+      const int ksteps = p.KC >> 4;
+      if (p.halo) {
+        if (ksteps == 4) mma_role_halo<4>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
+        else if (ksteps == 2) mma_role_halo<2>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
+        else mma_role_halo<1>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
+      } else {
+        if (ksteps == 4) mma_role<4>(p, smem_base, tmem_base, total_tiles, kblocks, s_full, s_empty, s_tfull, s_tempty);
+        else if (ksteps == 2) mma_role<2>(p, smem_base, tmem_base, total_tiles, kblocks, s_full, s_empty, s_tfull, s_tempty);
+        else mma_role<1>(p, smem_base, tmem_base, total_tiles, kblocks, s_full, s_empty, s_tfull, s_tempty);
       }
     }
   } else {
     // ===================================================================== epilogue (4 warps)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    // normal mode: rows ordered [n][h][w]; halo mode: [h][n][w] with w = 8
     const int wi = row & ((1 << p.lbw) - 1);
-    const int hi = (row >> p.lbw) & ((1 << p.lbh) - 1);
-    const int ni = row >> (p.lbw + p.lbh);
+    const int hi = p.halo ? (row >> (3 + p.lbn)) : ((row >> p.lbw) & ((1 << p.lbh) - 1));
+    const int ni = p.halo ? ((row >> 3) & ((1 << p.lbn) - 1)) : (row >> (p.lbw + p.lbh));
+    const int bn_shift = p.halo ? p.lbn : (7 - p.lbw - p.lbh);
     const int esize = p.out_bf16 ? 2 : 4;
     int j = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
@@ -237,7 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tw = mt % p.tiles_w; mt /= p.tiles_w;
       const int th = mt % p.tiles_h;
       const int tn = mt / p.tiles_h;
-      const int n = (tn << (7 - p.lbw - p.lbh)) + ni;
+      const int n = (tn << bn_shift) + ni;
       const int my = (th << p.lbh) + hi;
       const int mx = (tw << p.lbw) + wi;
       const bool valid = n < p.N;
@@ -346,6 +446,10 @@ int pow2_divisor(int v, int cap) { int d = 1; while (d * 2 <= cap && v % (d * 2)
 
 }  // namespace
 
+bool tc_halo_enabled() {
+  static const bool on = [] { const char* e = getenv("KFN_TC_HALO"); return !(e && e[0] == '0'); }();
+  return on;
+}
 int tc_pick_kc(int Cin) { return (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16; }
 int tc_cout_padded(int Cout) { return (Cout + 15) / 16 * 16; }
 
@@ -368,48 +472,86 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
 
   const int KC = tc_pick_kc(g.Cin);
   const int BN = CoutP < 256 ? CoutP : 256;
-  const int bw = pow2_divisor(g.MW, 128);
-  const int bh = pow2_divisor(g.MH, 128 / bw);
-  const int bn = 128 / (bw * bh);
-  p.lbw = ilog2(bw); p.lbh = ilog2(bh);
-  p.tiles_w = g.MW / bw; p.tiles_h = g.MH / bh; p.tiles_n = (g.N + bn - 1) / bn;
-  p.n_tiles = CoutP / BN;
+  const int row_bytes = KC * 2;                       // == swizzle span
+  const uint32_t layout_type = (KC == 64) ? 2u : (KC == 32) ? 4u : 6u;   // SWIZZLE_128B / 64B / 32B
+  const CUtensorMapSwizzle swz = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : (KC == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  const cuuint64_t cs = (cuuint64_t)g.in_cs * 2;      // bytes per pixel
+
+  // ---- halo mode eligibility: stride-1 3x3, 8-wide tiles, one N tile, weights resident in smem
+  bool halo = tc_halo_enabled() && g.istride == 1 && g.omul == 1 && g.ntaps >= 2 && CoutP <= 256 && g.MW % 8 == 0 &&
+              g.IH == g.MH && g.IW == g.MW && g.epi != EPI_L2NORM;
+  for (int t = 0; t < g.ntaps; ++t) halo = halo && g.dy[t] >= -1 && g.dy[t] <= 1 && g.dx[t] >= -1 && g.dx[t] <= 1;
+  int hbh = 0, hbn = 0;
+  if (halo) {
+    if (g.MH % 16 == 0) { hbh = 16; hbn = 1; }
+    else if (g.MH % 8 == 0) { hbh = 8; hbn = 2; }
+    else halo = false;
+  }
+  const uint32_t w_tile_bytes = ((uint32_t)(BN * row_bytes) + 1023u) & ~1023u;
+  const uint32_t w_total = (uint32_t)(g.ntaps * (g.Cin / KC)) * w_tile_bytes;
+  if (halo && w_total > 100 * 1024) halo = false;
+
   p.N = g.N; p.MH = g.MH; p.MW = g.MW;
   p.istride = g.istride; p.in_cs = g.in_cs;
   p.ntaps = g.ntaps;
   for (int t = 0; t < g.ntaps; ++t) { p.dy[t] = g.dy[t]; p.dx[t] = g.dx[t]; }
   p.kchunks = g.Cin / KC; p.KC = KC; p.BN = BN;
-  const int row_bytes = KC * 2;                       // == swizzle span
-  const uint32_t layout_type = (KC == 64) ? 2u : (KC == 32) ? 4u : 6u;   // SWIZZLE_128B / 64B / 32B
+  p.n_tiles = CoutP / BN;
   const uint32_t sbo16 = (uint32_t)(8 * row_bytes) >> 4;
   p.desc_hi = sbo16 | (1u << 14) | (layout_type << 29);   // bits 32-45 SBO, 46 version=1, 61-63 layout
+  p.desc_hi_halo = ((uint32_t)(10 * row_bytes) >> 4) | (1u << 14) | (layout_type << 29);
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-  p.a_bytes = (uint32_t)(kBlockM * row_bytes);
   p.b_bytes = (uint32_t)(BN * row_bytes);
-  p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
-  const uint32_t budget = 200 * 1024;
-  int stages = (int)(budget / p.stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  KFN_REQUIRE(stages >= 2, "pipeline needs at least 2 stages");
-  p.stages = stages;
+  p.row_bytes = row_bytes;
   p.OH = g.OH; p.OW = g.OW; p.out_cs = g.out_cs; p.out_coff = g.out_coff; p.Cout = g.Cout;
   p.omul = g.omul; p.oaddy = g.oaddy; p.oaddx = g.oaddx; p.relu = g.relu; p.epi = g.epi; p.out_bf16 = out_bf16;
   p.out = out; p.bias = bias_padded;
   if (g.epi == EPI_L2NORM) KFN_REQUIRE(BN == 32 && g.Cout == 32 && !out_bf16 && g.out_cs % 4 == 0, "l2norm epilogue shape");
 
-  const CUtensorMapSwizzle swz = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B
-                               : (KC == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-  // ---- A: 5-D view of the NHWC bf16 activation buffer
+  const uint32_t budget = 200 * 1024;
   cuuint64_t dimA[5], strA[4];
-  cuuint32_t boxA[5] = {(cuuint32_t)KC, (cuuint32_t)bw, 1u, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  const cuuint64_t cs = (cuuint64_t)g.in_cs * 2;      // bytes per pixel
-  if (g.istride == 1) {
-    dimA[0] = g.Cin; dimA[1] = g.IW; dimA[2] = 1; dimA[3] = g.IH; dimA[4] = g.N;
-    strA[0] = cs; strA[1] = cs * g.IW; strA[2] = cs * g.IW; strA[3] = cs * g.IW * g.IH;
+  cuuint32_t boxA[5];
+  if (halo) {
+    p.halo = 1;
+    p.lbw = 3; p.lbh = ilog2(hbh); p.lbn = ilog2(hbn);
+    p.tiles_w = g.MW / 8; p.tiles_h = g.MH / hbh; p.tiles_n = (g.N + hbn - 1) / hbn;
+    p.a_bytes = (uint32_t)(10 * hbn * (hbh + 2) * row_bytes);
+    p.stage_bytes = (p.a_bytes + 1023u) & ~1023u;
+    p.w_tile_bytes = w_tile_bytes; p.w_bytes_total = w_total;
+    for (int t = 0; t < g.ntaps; ++t)
+      p.tap_off16[t] = (uint32_t)(((1 + g.dy[t]) * 10 * hbn + (1 + g.dx[t])) * row_bytes) >> 4;
+    int stages = (int)((budget - w_total) / p.stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    KFN_REQUIRE(stages >= 2, "halo pipeline needs at least 2 stages");
+    p.stages = stages;
+    plan->smem = (size_t)w_total + (size_t)stages * p.stage_bytes + 1024;
+    // halo view: dims (c, w, n, h, 1) so that the box lands in smem as [y][n][x] rows
+    dimA[0] = g.Cin; dimA[1] = g.IW; dimA[2] = g.N; dimA[3] = g.IH; dimA[4] = 1;
+    strA[0] = cs; strA[1] = cs * g.IW * g.IH; strA[2] = cs * g.IW; strA[3] = cs * g.IW * g.IH * g.N;
+    boxA[0] = (cuuint32_t)KC; boxA[1] = 10; boxA[2] = (cuuint32_t)hbn; boxA[3] = (cuuint32_t)(hbh + 2); boxA[4] = 1;
   } else {
-    dimA[0] = (cuuint64_t)g.in_cs + g.Cin; dimA[1] = g.IW / 2; dimA[2] = 2; dimA[3] = g.IH / 2; dimA[4] = g.N;
-    strA[0] = cs * 2; strA[1] = cs * g.IW; strA[2] = cs * g.IW * 2; strA[3] = cs * g.IW * g.IH;
+    const int bw = pow2_divisor(g.MW, 128);
+    const int bh = pow2_divisor(g.MH, 128 / bw);
+    const int bn = 128 / (bw * bh);
+    p.lbw = ilog2(bw); p.lbh = ilog2(bh);
+    p.tiles_w = g.MW / bw; p.tiles_h = g.MH / bh; p.tiles_n = (g.N + bn - 1) / bn;
+    p.a_bytes = (uint32_t)(kBlockM * row_bytes);
+    p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
+    int stages = (int)(budget / p.stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    KFN_REQUIRE(stages >= 2, "pipeline needs at least 2 stages");
+    p.stages = stages;
+    plan->smem = (size_t)p.stages * p.stage_bytes + 1024;
+    boxA[0] = (cuuint32_t)KC; boxA[1] = (cuuint32_t)bw; boxA[2] = 1u; boxA[3] = (cuuint32_t)bh; boxA[4] = (cuuint32_t)bn;
+    if (g.istride == 1) {
+      dimA[0] = g.Cin; dimA[1] = g.IW; dimA[2] = 1; dimA[3] = g.IH; dimA[4] = g.N;
+      strA[0] = cs; strA[1] = cs * g.IW; strA[2] = cs * g.IW; strA[3] = cs * g.IW * g.IH;
+    } else {
+      dimA[0] = (cuuint64_t)g.in_cs + g.Cin; dimA[1] = g.IW / 2; dimA[2] = 2; dimA[3] = g.IH / 2; dimA[4] = g.N;
+      strA[0] = cs * 2; strA[1] = cs * g.IW; strA[2] = cs * g.IW * 2; strA[3] = cs * g.IW * g.IH;
+    }
   }
   CUresult r = encode(tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dimA, strA, boxA, ones,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -425,7 +567,6 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
 
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   plan->grid = total_tiles < num_sms ? total_tiles : num_sms;
-  plan->smem = (size_t)p.stages * p.stage_bytes + 1024;
   return KFN_OK;
 }
 

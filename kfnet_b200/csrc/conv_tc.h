@@ -11,6 +11,7 @@ struct TcConvPlan {
   size_t smem;
 };
 
+bool tc_halo_enabled();           // KFN_TC_HALO=0 disables the halo-tile variant (A/B measurements)
 int tc_pick_kc(int Cin);          // channels per k-block: 64 / 32 / 16 (128B / 64B / 32B swizzle)
 int tc_cout_padded(int Cout);     // weights are packed [tap][CoutP][Cin] bf16 with CoutP = roundup(Cout, 16)
 
