@@ -30,6 +30,7 @@ constexpr int kBlockM = 128;
 constexpr int kMaxStages = 12;
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kEpiStageBytes = 4 * 4096;            // per epilogue warp: 32 rows x 128 B staging for coalesced stores
 constexpr long long kWatchdogCycles = 4000000000ll;   // ~2 s at 1.9 GHz: trap instead of hanging the GPU
 
 struct __align__(8) TcParams {
@@ -54,6 +55,7 @@ struct __align__(8) TcParams {
   int halo, lbn, row_bytes;
   uint32_t desc_hi_halo;        // A descriptor upper word with SBO = 10 rows
   uint32_t w_tile_bytes, w_bytes_total;
+  uint32_t epi_stage_off;       // byte offset (from the 1024-aligned smem base) of the epilogue staging area
   uint32_t tap_off16[9];        // halo: ((1+dy) * 10*bn + (1+dx)) * row_bytes / 16 per tap
 };
 
@@ -127,6 +129,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -330,6 +341,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ni = p.halo ? ((row >> 3) & ((1 << p.lbn) - 1)) : (row >> (p.lbw + p.lbh));
     const int bn_shift = p.halo ? p.lbn : (7 - p.lbw - p.lbh);
     const int esize = p.out_bf16 ? 2 : 4;
+    // coalesced 64-column path: bf16 output, no special epilogue, 16-byte aligned rows / channel offsets
+    const bool fast64 = p.out_bf16 && p.epi == EPI_NONE && p.BN >= 64 && ((p.out_cs * 2) & 15) == 0 &&
+                        ((p.out_coff * 2) & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_stage_off + (uint32_t)quad * 4096u;
     int j = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const int nt = tile % p.n_tiles;
@@ -366,7 +381,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             dst[q] = make_float4(v[4 * q] * inv, v[4 * q + 1] * inv, v[4 * q + 2] * inv, v[4 * q + 3] * inv);
         }
       } else {
-        for (int nc = 0; nc < p.BN; nc += 16) {
+        int nc = 0;
+        if (fast64) {
+          // destination row pointers of the rows this lane WRITES in the coalesced pass: rows i*4 + lane/8
+          uint8_t* wrow[8];
+          bool wvalid[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int src = i * 4 + (lane >> 3);
+            const uint64_t ptr = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(orow), src);
+            wrow[i] = reinterpret_cast<uint8_t*>(ptr);
+            wvalid[i] = __shfl_sync(0xffffffffu, valid ? 1 : 0, src) != 0;
+          }
+          for (; nc + 64 <= p.BN && col0 + nc + 64 <= p.Cout; nc += 64) {
+            uint32_t r[64];
+            tmem_ld64(taddr + nc, r);
+            const int c = col0 + nc;
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
+            uint4 o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b0 = __ldg(b4 + 2 * q), b1 = __ldg(b4 + 2 * q + 1);
+              float v0 = __uint_as_float(r[8 * q + 0]) + b0.x, v1 = __uint_as_float(r[8 * q + 1]) + b0.y;
+              float v2 = __uint_as_float(r[8 * q + 2]) + b0.z, v3 = __uint_as_float(r[8 * q + 3]) + b0.w;
+              float v4 = __uint_as_float(r[8 * q + 4]) + b1.x, v5 = __uint_as_float(r[8 * q + 5]) + b1.y;
+              float v6 = __uint_as_float(r[8 * q + 6]) + b1.z, v7 = __uint_as_float(r[8 * q + 7]) + b1.w;
+              if (p.relu) {
+                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+                v4 = fmaxf(v4, 0.f); v5 = fmaxf(v5, 0.f); v6 = fmaxf(v6, 0.f); v7 = fmaxf(v7, 0.f);
+              }
+              o[q] = make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
+            }
+            // stage: row = lane, 16-byte chunk q at (q ^ (lane & 7)) -> conflict-free both ways
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = o[q];
+            __syncwarp();
+            const int cq = lane & 7;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + (lane >> 3);
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cq ^ (rr & 7)) << 4));
+              if (wvalid[i]) *reinterpret_cast<uint4*>(wrow[i] + (int64_t)c * 2 + cq * 16) = val;
+            }
+            __syncwarp();
+          }
+        }
+        for (; nc < p.BN; nc += 16) {
           float v[16];
           tmem_ld16(taddr + nc, v);
           const int c = col0 + nc;
@@ -526,7 +587,8 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     if (stages > kMaxStages) stages = kMaxStages;
     KFN_REQUIRE(stages >= 2, "halo pipeline needs at least 2 stages");
     p.stages = stages;
-    plan->smem = (size_t)w_total + (size_t)stages * p.stage_bytes + 1024;
+    p.epi_stage_off = w_total + (uint32_t)stages * p.stage_bytes;
+    plan->smem = (size_t)p.epi_stage_off + kEpiStageBytes + 1024;
     // halo view: dims (c, w, n, h, 1) so that the box lands in smem as [y][n][x] rows
     dimA[0] = g.Cin; dimA[1] = g.IW; dimA[2] = g.N; dimA[3] = g.IH; dimA[4] = 1;
     strA[0] = cs; strA[1] = cs * g.IW * g.IH; strA[2] = cs * g.IW; strA[3] = cs * g.IW * g.IH * g.N;
@@ -543,7 +605,8 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     if (stages > kMaxStages) stages = kMaxStages;
     KFN_REQUIRE(stages >= 2, "pipeline needs at least 2 stages");
     p.stages = stages;
-    plan->smem = (size_t)p.stages * p.stage_bytes + 1024;
+    p.epi_stage_off = (uint32_t)p.stages * p.stage_bytes;
+    plan->smem = (size_t)p.epi_stage_off + kEpiStageBytes + 1024;
     boxA[0] = (cuuint32_t)KC; boxA[1] = (cuuint32_t)bw; boxA[2] = 1u; boxA[3] = (cuuint32_t)bh; boxA[4] = (cuuint32_t)bn;
     if (g.istride == 1) {
       dimA[0] = g.Cin; dimA[1] = g.IW; dimA[2] = 1; dimA[3] = g.IH; dimA[4] = g.N;
@@ -573,7 +636,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
 int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024 + 1024));
+    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024 + 1024 + (int)kEpiStageBytes));
     attr_set = true;
   }
   const CUtensorMap* tmA = reinterpret_cast<const CUtensorMap*>(plan.blob);
