@@ -12,8 +12,8 @@
 //   accumulators live in TMEM (2 stages x 256 fp32 columns), drained by 4 epilogue warps with tcgen05.ld
 //   while the next tile's MMAs run; bias + ReLU (+ exp / l2-normalise) fused into the epilogue.
 //
-// One persistent CTA per SM (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).
+// One persistent CTA per SM (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; the two warps of a quadrant split the columns).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -28,9 +28,10 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kMaxStages = 12;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiWarps = 8;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kEpiStageBytes = 4 * 4096;            // per epilogue warp: 32 rows x 128 B staging for coalesced stores
+constexpr uint32_t kEpiStageBytes = kEpiWarps * 2048;     // per epilogue warp: 32 rows x 64 B staging for coalesced stores
 constexpr long long kWatchdogCycles = 4000000000ll;   // ~2 s at 1.9 GHz: trap instead of hanging the GPU
 
 struct __align__(8) TcParams {
@@ -55,6 +56,7 @@ struct __align__(8) TcParams {
   int halo, lbn, row_bytes;
   uint32_t desc_hi_halo;        // A descriptor upper word with SBO = 10 rows
   uint32_t w_tile_bytes, w_bytes_total;
+  int pf_dist;                  // L2 prefetch distance in tiles (0 = off)
   uint32_t epi_stage_off;       // byte offset (from the 1024-aligned smem base) of the epilogue staging area
   uint32_t tap_off16[9];        // halo: ((1+dy) * 10*bn + (1+dx)) * row_bytes / 16 per tap
 };
@@ -91,6 +93,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+// L2 prefetch of a future tile's box: raises the bytes in flight per SM beyond what the smem stages hold (Little's law
+// against multi-microsecond DRAM latency) without spending shared memory.
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
@@ -131,6 +140,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\t"
@@ -144,6 +162,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+
+// ------------------------------------------------------------------------------------------ tile iteration
+// Each persistent CTA owns a contiguous, balanced range of tiles (n-tile fastest, then w, h, n) and walks it with
+// incremental coordinate updates: the integer divisions of the decode happen once per CTA, not once per tile per
+// role (profiles/r01c: the per-tile div/mod + pointer arithmetic was ~1900 cycles on the epilogue's critical path).
+struct TileIter {
+  int tile, end, nt, tw, th, tn;
+  __device__ __forceinline__ void init(const TcParams& p, int total) {
+    const int base = total / (int)gridDim.x, rem = total % (int)gridDim.x, b = (int)blockIdx.x;
+    tile = b * base + (b < rem ? b : rem);
+    end = tile + base + (b < rem ? 1 : 0);
+    nt = tile % p.n_tiles;
+    int mt = tile / p.n_tiles;
+    tw = mt % p.tiles_w; mt /= p.tiles_w;
+    th = mt % p.tiles_h;
+    tn = mt / p.tiles_h;
+  }
+  __device__ __forceinline__ bool valid() const { return tile < end; }
+  __device__ __forceinline__ void next(const TcParams& p) {
+    ++tile;
+    if (++nt == p.n_tiles) { nt = 0; if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } } }
+  }
+};
 
 // ------------------------------------------------------------------------------------------ MMA issuer roles
 // Descriptors are 64-bit values advanced with adds of precomputed constants (start address field is in 16-byte
@@ -159,7 +200,8 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint32_t smem_base, 
   int s = 0, j = 0;
   uint32_t ph = 0;
   uint64_t adesc = a0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+  TileIter it;
+  for (it.init(p, total_tiles); it.valid(); it.next(p), ++j) {
     const int a = j & 1;
     const uint32_t aph = (uint32_t)(j >> 1) & 1u;
     mbar_wait(smem_u32(&s_tempty[a]), aph ^ 1u);
@@ -192,7 +234,8 @@ __device__ __forceinline__ void mma_role_halo(const TcParams& p, uint32_t smem_b
   int s = 0, j = 0;
   uint32_t ph = 0;
   uint64_t adesc = a0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+  TileIter it;
+  for (it.init(p, total_tiles); it.valid(); it.next(p), ++j) {
     const int a = j & 1;
     const uint32_t aph = (uint32_t)(j >> 1) & 1u;
     mbar_wait(smem_u32(&s_tempty[a]), aph ^ 1u);
@@ -239,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&s_tfull[a]), 1);
-      mbar_init(smem_u32(&s_tempty[a]), 4);
+      mbar_init(smem_u32(&s_tempty[a]), kEpiWarps);
     }
     mbar_init(smem_u32(&s_wbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -276,12 +319,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t stage0 = smem_base + p.w_bytes_total;
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int mt = tile;
-        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-        const int th = mt % p.tiles_h;
-        const int tn = mt / p.tiles_h;
-        const int w0 = tw << 3, h0 = th << p.lbh, n0 = tn << p.lbn;
+      TileIter it, pf;
+      pf.init(p, total_tiles);
+      for (int d = 0; d < p.pf_dist && pf.valid(); ++d, pf.next(p))
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_prefetch_5d(&tmA, kc * p.KC, (pf.tw << 3) - 1, pf.tn << p.lbn, (pf.th << p.lbh) - 1, 0);
+      for (it.init(p, total_tiles); it.valid(); it.next(p)) {
+        const int w0 = it.tw << 3, h0 = it.th << p.lbh, n0 = it.tn << p.lbn;
+        if (p.pf_dist && pf.valid()) {
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            tma_prefetch_5d(&tmA, kc * p.KC, (pf.tw << 3) - 1, pf.tn << p.lbn, (pf.th << p.lbh) - 1, 0);
+          pf.next(p);
+        }
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);
           const uint32_t full = smem_u32(&s_full[s]);
@@ -293,13 +342,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        int mt = tile / p.n_tiles;
-        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-        const int th = mt % p.tiles_h;
-        const int tn = mt / p.tiles_h;
-        const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << (7 - p.lbw - p.lbh);
+      TileIter it, pf;
+      pf.init(p, total_tiles);
+      // prefetch the centre-tap box of future tiles (the other taps overlap it except for a 1-pixel rim)
+      auto prefetch_tile = [&](const TileIter& t) {
+        if (t.nt != 0) return;
+        const int pw = t.tw << p.lbw, phh = t.th << p.lbh, pn = t.tn << (7 - p.lbw - p.lbh);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          if (p.istride == 1) tma_prefetch_5d(&tmA, kc * p.KC, pw, 0, phh, pn);
+          else { tma_prefetch_5d(&tmA, kc * p.KC, pw, 0, phh, pn); tma_prefetch_5d(&tmA, p.in_cs + kc * p.KC, pw, 1, phh, pn); }
+        }
+      };
+      for (int d = 0; d < p.pf_dist && pf.valid(); ++d, pf.next(p)) prefetch_tile(pf);
+      for (it.init(p, total_tiles); it.valid(); it.next(p)) {
+        const int nt = it.nt;
+        const int w0 = it.tw << p.lbw, h0 = it.th << p.lbh, n0 = it.tn << (7 - p.lbw - p.lbh);
+        if (p.pf_dist && pf.valid()) { prefetch_tile(pf); pf.next(p); }
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int dy = p.dy[tap], dx = p.dx[tap];
           int cw, cpar, chh, coff;
@@ -332,75 +390,82 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================================================================== epilogue (4 warps)
+    // ===================================================================== epilogue (8 warps)
+    // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the column blocks.
     const int quad = warp & 3;
+    const int hsel = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
-    // normal mode: rows ordered [n][h][w]; halo mode: [h][n][w] with w = 8
-    const int wi = row & ((1 << p.lbw) - 1);
-    const int hi = p.halo ? (row >> (3 + p.lbn)) : ((row >> p.lbw) & ((1 << p.lbh) - 1));
-    const int ni = p.halo ? ((row >> 3) & ((1 << p.lbn) - 1)) : (row >> (p.lbw + p.lbh));
     const int bn_shift = p.halo ? p.lbn : (7 - p.lbw - p.lbh);
     const int esize = p.out_bf16 ? 2 : 4;
-    // coalesced 64-column path: bf16 output, no special epilogue, 16-byte aligned rows / channel offsets
-    const bool fast64 = p.out_bf16 && p.epi == EPI_NONE && p.BN >= 64 && ((p.out_cs * 2) & 15) == 0 &&
-                        ((p.out_coff * 2) & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-    uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_stage_off + (uint32_t)quad * 4096u;
+    // coalesced 32-column path: bf16 output, no special epilogue, 16-byte aligned rows / channel offsets
+    const bool fast32 = p.out_bf16 && p.epi == EPI_NONE && ((p.out_cs * 2) & 15) == 0 && ((p.out_coff * 2) & 15) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_stage_off + (uint32_t)(warp - 2) * 2048u;
+    // tile-invariant part of every row's output offset (bytes): computed once per thread.
+    // normal mode: rows ordered [n][h][w]; halo mode: [h][n][w] with w = 8
+    auto row_off = [&](int r, int& r_ni) -> int64_t {
+      const int r_wi = r & ((1 << p.lbw) - 1);
+      const int r_hi = p.halo ? (r >> (3 + p.lbn)) : ((r >> p.lbw) & ((1 << p.lbh) - 1));
+      r_ni = p.halo ? ((r >> 3) & ((1 << p.lbn) - 1)) : (r >> (p.lbw + p.lbh));
+      return (((int64_t)r_ni * p.OH + r_hi * p.omul) * p.OW + r_wi * p.omul) * p.out_cs * esize;
+    };
+    int my_ni;
+    const int64_t my_off = row_off(row, my_ni);
+    int64_t wr_off[4];      // rows this lane writes in the coalesced pass: quad*32 + i*8 + lane/4
+    int wr_ni[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wr_off[i] = row_off(quad * 32 + i * 8 + (lane >> 2), wr_ni[i]);
+    const int sw_st = (lane >> 1) & 3;        // staging swizzle of this lane's own row (64-byte rows, 2 per bank row)
+    const int cq = lane & 3;
     int j = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
-      const int nt = tile % p.n_tiles;
-      int mt = tile / p.n_tiles;
-      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-      const int th = mt % p.tiles_h;
-      const int tn = mt / p.tiles_h;
-      const int n = (tn << bn_shift) + ni;
-      const int my = (th << p.lbh) + hi;
-      const int mx = (tw << p.lbw) + wi;
-      const bool valid = n < p.N;
-      const int64_t opix = ((int64_t)n * p.OH + my * p.omul + p.oaddy) * p.OW + mx * p.omul + p.oaddx;
-      uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) + (opix * p.out_cs + p.out_coff) * esize;
+    TileIter it;
+    for (it.init(p, total_tiles); it.valid(); it.next(p), ++j) {
+      const int n0 = it.tn << bn_shift;
+      const int64_t tile_off = ((((int64_t)n0 * p.OH + (it.th << p.lbh) * p.omul + p.oaddy) * p.OW +
+                                 (it.tw << p.lbw) * p.omul + p.oaddx) * p.out_cs + p.out_coff) * esize;
+      uint8_t* const tile_ptr = reinterpret_cast<uint8_t*>(p.out) + tile_off;
+      const bool valid = n0 + my_ni < p.N;
+      uint8_t* const orow = tile_ptr + my_off;
       const int a = j & 1;
       const uint32_t aph = (uint32_t)(j >> 1) & 1u;
       mbar_wait(smem_u32(&s_tfull[a]), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)a * 256u;
-      const int col0 = nt * p.BN;
+      const int col0 = it.nt * p.BN;
 
       if (p.epi == EPI_L2NORM) {
-        // feat7: BN == Cout == 32, fp32 output, x * rsqrt(max(sum x^2, 1e-12))  (KFNet/KFNet.py:340)
-        float v[32];
-        tmem_ld16(taddr, v);
-        tmem_ld16(taddr + 16, v + 16);
-        float ss = 0.f;
+        if (hsel == 0) {
+          // feat7: BN == Cout == 32, fp32 output, x * rsqrt(max(sum x^2, 1e-12))  (KFNet/KFNet.py:340)
+          uint32_t r[32];
+          tmem_ld32(taddr, r);
+          float v[32];
+          float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { v[i] += __ldg(p.bias + i); ss += v[i] * v[i]; }
-        const float inv = rsqrtf(fmaxf(ss, 1e-12f));
-        if (valid) {
-          float4* dst = reinterpret_cast<float4*>(orow);
+          for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r[i]) + __ldg(p.bias + i); ss += v[i] * v[i]; }
+          const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(orow);
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            dst[q] = make_float4(v[4 * q] * inv, v[4 * q + 1] * inv, v[4 * q + 2] * inv, v[4 * q + 3] * inv);
+            for (int q = 0; q < 8; ++q)
+              dst[q] = make_float4(v[4 * q] * inv, v[4 * q + 1] * inv, v[4 * q + 2] * inv, v[4 * q + 3] * inv);
+          }
         }
       } else {
         int nc = 0;
-        if (fast64) {
-          // destination row pointers of the rows this lane WRITES in the coalesced pass: rows i*4 + lane/8
-          uint8_t* wrow[8];
-          bool wvalid[8];
+        if (fast32) {
+          uint8_t* wrow[4];
+          bool wvalid[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int src = i * 4 + (lane >> 3);
-            const uint64_t ptr = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(orow), src);
-            wrow[i] = reinterpret_cast<uint8_t*>(ptr);
-            wvalid[i] = __shfl_sync(0xffffffffu, valid ? 1 : 0, src) != 0;
-          }
-          for (; nc + 64 <= p.BN && col0 + nc + 64 <= p.Cout; nc += 64) {
-            uint32_t r[64];
-            tmem_ld64(taddr + nc, r);
+          for (int i = 0; i < 4; ++i) { wrow[i] = tile_ptr + wr_off[i]; wvalid[i] = n0 + wr_ni[i] < p.N; }
+          for (; nc + 32 <= p.BN && col0 + nc + 32 <= p.Cout; nc += 32) {
+            if (((nc >> 5) & 1) != hsel) continue;
+            uint32_t r[32];
+            tmem_ld32(taddr + nc, r);
             const int c = col0 + nc;
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
-            uint4 o[8];
+            // stage: row = lane (64 B), 16-byte chunk q at slot q ^ ((lane >> 1) & 3): conflict-free both ways
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
               const float4 b0 = __ldg(b4 + 2 * q), b1 = __ldg(b4 + 2 * q + 1);
               float v0 = __uint_as_float(r[8 * q + 0]) + b0.x, v1 = __uint_as_float(r[8 * q + 1]) + b0.y;
               float v2 = __uint_as_float(r[8 * q + 2]) + b0.z, v3 = __uint_as_float(r[8 * q + 3]) + b0.w;
@@ -410,24 +475,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
                 v4 = fmaxf(v4, 0.f); v5 = fmaxf(v5, 0.f); v6 = fmaxf(v6, 0.f); v7 = fmaxf(v7, 0.f);
               }
-              o[q] = make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw_st) << 4)) =
+                  make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
             }
-            // stage: row = lane, 16-byte chunk q at (q ^ (lane & 7)) -> conflict-free both ways
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = o[q];
             __syncwarp();
-            const int cq = lane & 7;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = i * 4 + (lane >> 3);
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cq ^ (rr & 7)) << 4));
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + (lane >> 2);
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((cq ^ ((rr >> 1) & 3)) << 4));
               if (wvalid[i]) *reinterpret_cast<uint4*>(wrow[i] + (int64_t)c * 2 + cq * 16) = val;
             }
             __syncwarp();
           }
         }
         for (; nc < p.BN; nc += 16) {
+          if (((nc >> 4) & 1) != hsel) continue;
           float v[16];
           tmem_ld16(taddr + nc, v);
           const int c = col0 + nc;
@@ -509,6 +571,10 @@ int pow2_divisor(int v, int cap) { int d = 1; while (d * 2 <= cap && v % (d * 2)
 
 bool tc_halo_enabled() {
   static const bool on = [] { const char* e = getenv("KFN_TC_HALO"); return !(e && e[0] == '0'); }();
+  return on;
+}
+bool tc_prefetch_enabled() {
+  static const bool on = [] { const char* e = getenv("KFN_TC_PREFETCH"); return e && e[0] == '1'; }();
   return on;
 }
 int tc_pick_kc(int Cin) { return (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16; }
@@ -628,6 +694,15 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); return KFN_ERR_CUDA; }
 
+  {
+    // prefetch only for memory/latency-bound shapes (few k-blocks per tile); ~384 KB ahead per SM
+    const int kblocks = g.ntaps * p.kchunks;
+    const uint32_t bytes_per_tile = p.a_bytes * (uint32_t)p.kchunks;
+    int dist = (int)((384u * 1024u) / (bytes_per_tile ? bytes_per_tile : 1u));
+    if (dist > 64) dist = 64;
+    if (dist < 2) dist = 2;
+    p.pf_dist = (tc_prefetch_enabled() && (halo || kblocks <= 18)) ? dist : 0;
+  }
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   plan->grid = total_tiles < num_sms ? total_tiles : num_sms;
   return KFN_OK;
