@@ -95,59 +95,69 @@ int launch_l2norm32(float* x, int64_t rows, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // Feature-difference volume (KFNet.BuildCoordVolume, KFNet/KFNet.py:343-359, reshape :372):
 //   diff[n, p, i, j, c] = f_cur[n,p,c] - f_prev[n, p + (ox,oy), c],  (ox,oy) = (j-4, i-4), 0 outside.
-// One thread produces 16 bytes of output (4 fp32 or 8 bf16 channels); consecutive threads write
-// consecutive 16-byte words, so every warp store is one fully-coalesced 512-byte run.
+// One warp per label pixel.  A lane owns a channel group (CH channels = 16 output bytes) and a sub-offset; f_cur stays
+// in registers, the loop over the remaining offsets is fully unrolled (all neighbour loads in flight at once), and
+// every store instruction of the warp writes one contiguous 512-byte run.  ~15 instructions per 16 bytes stored
+// (the first version decoded (n,p,k,g) per thread with div/mod: ~100 instructions, instruction bound at 45 % of HBM).
 template <bool kBf16>
-__global__ void diff_volume_kernel(const float* __restrict__ f_prev, const float* __restrict__ f_cur,
-                                   void* __restrict__ out, int NP, int GH, int GW) {
-  constexpr int CH = kBf16 ? 8 : 4;          // channels per thread
-  constexpr int GROUPS = 32 / CH;            // threads per (pixel, offset)
+__global__ void __launch_bounds__(256) diff_volume_kernel(const float* __restrict__ f_prev, const float* __restrict__ f_cur,
+                                                          uint4* __restrict__ out, int64_t npix, int GH, int GW) {
+  constexpr int CH = kBf16 ? 8 : 4;            // channels per lane
+  constexpr int GROUPS = 32 / CH;              // lanes per (pixel, offset)
+  constexpr int KSUB = 32 / GROUPS;            // offsets covered by one warp store
+  constexpr int ITERS = 64 / KSUB;
+  const int lane = threadIdx.x & 31;
+  const int g = lane % GROUPS, ksub = lane / GROUPS;
   const int P = GH * GW;
-  const int64_t total = (int64_t)NP * P * 64 * GROUPS;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; idx < total; idx += stride) {
-    int g = (int)(idx % GROUPS);
-    int k = (int)((idx / GROUPS) % 64);
-    int64_t np = idx / (GROUPS * 64);
-    int p = (int)(np % P);
-    int64_t n = np / P;
-    int y = p / GW, x = p - y * GW;
-    int yy = y + (k >> 3) - 4, xx = x + (k & 7) - 4;
-    bool inb = (yy >= 0) && (yy < GH) && (xx >= 0) && (xx < GW);
-    const float4* cur = reinterpret_cast<const float4*>(f_cur + (n * P + p) * 32 + g * CH);
-    const float4* prv = reinterpret_cast<const float4*>(f_prev + (n * P + (inb ? yy * GW + xx : 0)) * 32 + g * CH);
-    float4 a = __ldg(cur);
-    float4 b = inb ? __ldg(prv) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 d0 = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
-    if constexpr (!kBf16) {
-      reinterpret_cast<float4*>(out)[idx] = d0;
-    } else {
-      float4 a1 = __ldg(cur + 1);
-      float4 b1 = inb ? __ldg(prv + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(d0.x, d0.y);
-      __nv_bfloat162 h1 = __floats2bfloat162_rn(d0.z, d0.w);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(a1.x - b1.x, a1.y - b1.y);
-      __nv_bfloat162 h3 = __floats2bfloat162_rn(a1.z - b1.z, a1.w - b1.w);
+  int64_t np = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (; np < npix; np += wstride) {
+    const int p = (int)(np % P);
+    const int64_t nbase = np - p;                // n * P
+    const int y = p / GW, x = p - y * GW;
+    const float4* cur = reinterpret_cast<const float4*>(f_cur + np * 32 + g * CH);
+    const float4 a0 = __ldg(cur);
+    float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (kBf16) a1 = __ldg(cur + 1);
+    float4 b0[ITERS], b1[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int k = it * KSUB + ksub;
+      const int yy = y + (k >> 3) - 4, xx = x + (k & 7) - 4;
+      const bool inb = (yy >= 0) && (yy < GH) && (xx >= 0) && (xx < GW);
+      const float4* prv = reinterpret_cast<const float4*>(f_prev + (nbase + (inb ? yy * GW + xx : 0)) * 32 + g * CH);
+      b0[it] = inb ? __ldg(prv) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (kBf16) b1[it] = inb ? __ldg(prv + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint4* dst = out + np * 64 * GROUPS + lane;  // + it * 32 : consecutive lanes -> consecutive 16-byte words
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
       uint4 o;
-      o.x = *reinterpret_cast<uint32_t*>(&h0);
-      o.y = *reinterpret_cast<uint32_t*>(&h1);
-      o.z = *reinterpret_cast<uint32_t*>(&h2);
-      o.w = *reinterpret_cast<uint32_t*>(&h3);
-      reinterpret_cast<uint4*>(out)[idx] = o;
+      if constexpr (kBf16) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(a0.x - b0[it].x, a0.y - b0[it].y);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(a0.z - b0[it].z, a0.w - b0[it].w);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(a1.x - b1[it].x, a1.y - b1[it].y);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(a1.z - b1[it].z, a1.w - b1[it].w);
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+      } else {
+        o.x = __float_as_uint(a0.x - b0[it].x); o.y = __float_as_uint(a0.y - b0[it].y);
+        o.z = __float_as_uint(a0.z - b0[it].z); o.w = __float_as_uint(a0.w - b0[it].w);
+      }
+      __stcs(dst + it * 32, o);      // streaming store: the volume is written once and read once by conv0
     }
   }
 }
 
 int launch_diff_volume(const float* f_prev, const float* f_cur, int NP, int GH, int GW, void* diff, int out_bf16,
                        cudaStream_t st) {
-  int64_t total = (int64_t)NP * GH * GW * 64 * (out_bf16 ? 4 : 8);
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;   // grid-stride; multiple of the SM count
+  const int64_t npix = (int64_t)NP * GH * GW;     // one warp each
+  int64_t blocks = (npix + 7) / 8;
+  if (blocks > 148 * 64) blocks = 148 * 64;       // grid-stride beyond that; multiple of the SM count
   if (out_bf16)
-    diff_volume_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, diff, NP, GH, GW);
+    diff_volume_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, reinterpret_cast<uint4*>(diff), npix, GH, GW);
   else
-    diff_volume_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, diff, NP, GH, GW);
+    diff_volume_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, reinterpret_cast<uint4*>(diff), npix, GH, GW);
   KFN_LAUNCH_OK();
   return KFN_OK;
 }

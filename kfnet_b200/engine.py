@@ -91,10 +91,11 @@ class Engine:
         _lib.check(self.lib.kfn_oflow_feat_forward(self.h, _ptr(images), B, _ptr(out), _ptr(ws), ws.numel(), self._stream()))
         return out
 
-    def diff_volume(self, f_prev, f_cur, bf16=False):
+    def diff_volume(self, f_prev, f_cur, bf16=False, out=None):
         NP, GH, GW, Cc = f_prev.shape
         assert Cc == 32 and f_prev.dtype == torch.float32 and f_prev.is_contiguous() and f_cur.is_contiguous()
-        out = torch.empty(NP * GH * GW, 8, 8, 32, dtype=torch.bfloat16 if bf16 else torch.float32, device=f_prev.device)
+        if out is None:
+            out = torch.empty(NP * GH * GW, 8, 8, 32, dtype=torch.bfloat16 if bf16 else torch.float32, device=f_prev.device)
         _lib.check(self.lib.kfn_diff_volume(_ptr(f_prev), _ptr(f_cur), NP, GH, GW, _ptr(out), 1 if bf16 else 0, self._stream()))
         return out
 
