@@ -82,6 +82,28 @@ class Engine:
         _lib.check(self.lib.kfn_scoordnet_forward(self.h, _ptr(images), B, _ptr(out), _ptr(ws), ws.numel(), self._stream()))
         return out
 
+    # ---- the same, replayed from a CUDA graph (captured on first use for a given set of buffers / parameters):
+    #      removes the CPU launch cost and most of the inter-kernel gaps of the ~7000 launches of a 256-frame step ----
+    def eval_sequences_graphed(self, images, transform, out, reinit_period=500, nis_gate=False, frames_per_batch=8,
+                               pairs_per_batch=4):
+        key = (images.data_ptr(), out.data_ptr(), tuple(images.shape), int(reinit_period), bool(nis_gate),
+               int(frames_per_batch), int(pairs_per_batch), np.asarray(transform, dtype=np.float32).tobytes())
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        g = self._graphs.get(key)
+        if g is None:
+            # warm-up outside capture (workspace allocation, TMA descriptor cache, function attributes)
+            self.eval_sequences(images, transform, reinit_period, nis_gate, frames_per_batch, pairs_per_batch, out=out)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.eval_sequences(images, transform, reinit_period, nis_gate, frames_per_batch, pairs_per_batch, out=out)
+            if len(self._graphs) > 8:
+                self._graphs.clear()
+            self._graphs[key] = g
+        g.replay()
+        return out
+
     # ---- feature tower: images -> l2-normalised feat fp32 [B,GH,GW,32] ----
     def oflow_feat(self, images):
         self._chk_img(images)
