@@ -46,8 +46,12 @@ enum kfn_status {
  *                  reference (all reference arithmetic is fp32); used for the 1e-4 parity configs.
  *  KFN_MODE_BF16 : tcgen05.mma (kind::f16, bf16 operands, fp32 TMEM accumulators) fed by TMA; bf16
  *                  activations between layers; fp32 for everything after the conv stacks.  The
- *                  "bf16 compute / fp32 accumulate" configuration of BASELINE.json configs[3..4].      */
-enum kfn_mode { KFN_MODE_FP32 = 0, KFN_MODE_BF16 = 1 };
+ *                  "bf16 compute / fp32 accumulate" configuration of BASELINE.json configs[3..4].
+ *  KFN_MODE_BF16X3: the same tcgen05 kernel, error-compensated: activations and weights are carried as three bf16
+ *                  limbs (x = x1+x2+x3, 24 significant bits) and every layer accumulates the six limb products
+ *                  a1w1+a1w2+a2w1+a2w2+a1w3+a3w1 in fp32 TMEM -- fp32-grade results (the 1e-4 parity configs) on
+ *                  the tensor cores at 1/6 of the bf16 MMA rate.                                             */
+enum kfn_mode { KFN_MODE_FP32 = 0, KFN_MODE_BF16 = 1, KFN_MODE_BF16X3 = 2 };
 
 /* geometry of the path (KFNet/KFNet.py:7-16,70; eval.py:49-50) */
 #define KFN_IMG_H 480

@@ -56,6 +56,11 @@ struct ConvGeom {
   int omul, oaddy, oaddx;
   int relu;
   int epi;            // EPI_*
+  // error-compensated bf16x3 mode (0 is read as 1): activations / weights are stored as bf16 "limbs"
+  // x = x1 + x2 + x3 laid out [limb][channels] inside each pixel (limb stride in_ls / out_ls elements);
+  // the GEMM accumulates the limb products a1w1 + a1w2 + a2w1 + a2w2 + a1w3 + a3w1 in fp32.
+  int limbs_a, limbs_w, limbs_out;
+  int in_ls, out_ls;
 };
 enum { EPI_NONE = 0, EPI_EXP_CH3 = 1, EPI_L2NORM = 2 };
 
@@ -68,7 +73,7 @@ int launch_preprocess_f32(const uint8_t* img, float* out, int64_t n, cudaStream_
 int launch_im2col27_bf16(const uint8_t* img, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st);
 int launch_l2norm32(float* x, int64_t rows, cudaStream_t st);
 int launch_diff_volume(const float* f_prev, const float* f_cur, int NP, int GH, int GW, void* diff, int out_bf16,
-                       cudaStream_t st);
+                       cudaStream_t st);   // out_bf16: 0 fp32, 1 bf16, 3 three bf16 limbs [.., 3, 32]
 int launch_softmax_flow(const float* logits, const float* logsig, int logsig_stride, int64_t rows, float* flow,
                         float* sigma_w, int32_t* argmax, cudaStream_t st);
 int launch_kalman_scan(const float* measure, const float* flow, const float* sigma_w, const float* state_in,

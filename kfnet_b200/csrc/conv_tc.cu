@@ -57,6 +57,10 @@ struct __align__(8) TcParams {
   uint32_t desc_hi_halo;        // A descriptor upper word with SBO = 10 rows
   uint32_t w_tile_bytes, w_bytes_total;
   int pf_dist;                  // L2 prefetch distance in tiles (0 = off)
+  // bf16x3: k-chunks = n_terms x cpk; term t multiplies A limb la[t] with W limb lw[t]
+  int n_terms, cpk, in_ls, w_cin, out_limbs, out_ls;
+  int x3acc;                    // 1: four 128-column TMEM accumulators (3 main-term splits + corrections), single-buffered
+  int la[6], lw[6];
   uint32_t epi_stage_off;       // byte offset (from the 1024-aligned smem base) of the epilogue staging area
   uint32_t tap_off16[9];        // halo: ((1+dy) * 10*bn + (1+dx)) * row_bytes / 16 per tap
 };
@@ -260,6 +264,44 @@ __device__ __forceinline__ void mma_role_halo(const TcParams& p, uint32_t smem_b
   }
 }
 
+// bf16x3: the tensor core truncates (does not round) on every accumulation, a bias that grows with the length of
+// the accumulation chain (~n_mma * 2^-24).  Keep chains short and small terms separate: the main term a1*w1 goes
+// round-robin by tap into accumulators 0..2, all correction terms into accumulator 3; the epilogue adds the four
+// with round-to-nearest fp32.  Single-buffered (4 x 128 columns = all of TMEM).
+template <int KSTEPS>
+__device__ __forceinline__ void mma_role_x3(const TcParams& p, uint32_t smem_base, uint32_t tmem_base, int total_tiles,
+                                            uint64_t* s_full, uint64_t* s_empty, uint64_t* s_tfull, uint64_t* s_tempty) {
+  const uint64_t desc_fixed = ((uint64_t)p.desc_hi << 32) | (1ull << 16);
+  const uint64_t stage16 = (uint64_t)(p.stage_bytes >> 4);
+  const uint64_t a0 = desc_fixed | (uint64_t)(smem_base >> 4);
+  const uint64_t b_off = (uint64_t)(p.a_bytes >> 4);
+  int s = 0, j = 0;
+  uint32_t ph = 0;
+  uint64_t adesc = a0;
+  TileIter it;
+  for (it.init(p, total_tiles); it.valid(); it.next(p), ++j) {
+    mbar_wait(smem_u32(&s_tempty[0]), ((uint32_t)j & 1u) ^ 1u);
+    tc_fence_after();
+    uint32_t used = 0;
+    for (int tap = 0; tap < p.ntaps; ++tap) {
+      for (int t = 0; t < p.n_terms; ++t) {
+        const int acc = (p.la[t] == 0 && p.lw[t] == 0) ? (tap % 3) : 3;
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 128u;
+        for (int kc = 0; kc < p.cpk; ++kc) {
+          mbar_wait(smem_u32(&s_full[s]), ph);
+          tc_fence_after();
+          umma_kblock<KSTEPS>(tmem_d, adesc, adesc + b_off, p.idesc, (used >> acc) & 1u);
+          used |= 1u << acc;
+          umma_commit(smem_u32(&s_empty[s]));
+          adesc += stage16;
+          if (++s == p.stages) { s = 0; ph ^= 1u; adesc = a0; }
+        }
+      }
+    }
+    umma_commit(smem_u32(&s_tfull[0]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -363,14 +405,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int cw, cpar, chh, coff;
           if (p.istride == 1) { cw = w0 + dx; cpar = 0; chh = h0 + dy; coff = 0; }
           else { cw = w0 + (dx >> 1); cpar = dy & 1; chh = h0 + (dy >> 1); coff = (dx & 1) * p.in_cs; }
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);
-            const uint32_t full = smem_u32(&s_full[s]);
-            const uint32_t a_dst = smem_base + (uint32_t)s * p.stage_bytes;
-            mbar_expect_tx(full, p.a_bytes + p.b_bytes);
-            tma_load_5d(a_dst, &tmA, full, coff + kc * p.KC, cw, cpar, chh, n0);
-            tma_load_3d(a_dst + p.a_bytes, &tmB, full, kc * p.KC, nt * p.BN, tap);
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          for (int t = 0; t < p.n_terms; ++t) {
+            const int a_c0 = coff + p.la[t] * p.in_ls, w_c0 = p.lw[t] * p.w_cin;
+            for (int kc = 0; kc < p.cpk; ++kc) {
+              mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);
+              const uint32_t full = smem_u32(&s_full[s]);
+              const uint32_t a_dst = smem_base + (uint32_t)s * p.stage_bytes;
+              mbar_expect_tx(full, p.a_bytes + p.b_bytes);
+              tma_load_5d(a_dst, &tmA, full, a_c0 + kc * p.KC, cw, cpar, chh, n0);
+              tma_load_3d(a_dst + p.a_bytes, &tmB, full, w_c0 + kc * p.KC, nt * p.BN, tap);
+              if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
           }
         }
       }
@@ -379,7 +424,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================================== MMA issuer (one lane)
     if (lane == 0) {
       const int ksteps = p.KC >> 4;
-      if (p.halo) {
+      if (p.x3acc) {
+        if (ksteps == 4) mma_role_x3<4>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty);
+        else if (ksteps == 2) mma_role_x3<2>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty);
+        else mma_role_x3<1>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty);
+      } else if (p.halo) {
         if (ksteps == 4) mma_role_halo<4>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
         else if (ksteps == 2) mma_role_halo<2>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
         else mma_role_halo<1>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
@@ -399,6 +448,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int esize = p.out_bf16 ? 2 : 4;
     // coalesced 32-column path: bf16 output, no special epilogue, 16-byte aligned rows / channel offsets
     const bool fast32 = p.out_bf16 && p.epi == EPI_NONE && ((p.out_cs * 2) & 15) == 0 && ((p.out_coff * 2) & 15) == 0 &&
+                        ((p.out_ls * 2) & 15) == 0 &&
                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_stage_off + (uint32_t)(warp - 2) * 2048u;
     // tile-invariant part of every row's output offset (bytes): computed once per thread.
@@ -426,12 +476,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint8_t* const tile_ptr = reinterpret_cast<uint8_t*>(p.out) + tile_off;
       const bool valid = n0 + my_ni < p.N;
       uint8_t* const orow = tile_ptr + my_off;
-      const int a = j & 1;
-      const uint32_t aph = (uint32_t)(j >> 1) & 1u;
+      const int a = p.x3acc ? 0 : (j & 1);
+      const uint32_t aph = p.x3acc ? ((uint32_t)j & 1u) : ((uint32_t)(j >> 1) & 1u);
       mbar_wait(smem_u32(&s_tfull[a]), aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)a * 256u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (p.x3acc ? 0u : (uint32_t)a * 256u);
       const int col0 = it.nt * p.BN;
+      const int n_main = p.ntaps < 3 ? p.ntaps : 3;     // x3acc: main-term accumulators in use
 
       if (p.epi == EPI_L2NORM) {
         if (hsel == 0) {
@@ -441,7 +492,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[32];
           float ss = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r[i]) + __ldg(p.bias + i); ss += v[i] * v[i]; }
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.x3acc) {
+            for (int acc = 1; acc < 4; ++acc) {
+              if (acc < 3 && acc >= n_main) continue;
+              tmem_ld32(taddr + (uint32_t)acc * 128u, r);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[i] += __ldg(p.bias + i); ss += v[i] * v[i]; }
           const float inv = rsqrtf(fmaxf(ss, 1e-12f));
           if (valid) {
             float4* dst = reinterpret_cast<float4*>(orow);
@@ -463,35 +524,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32(taddr + nc, r);
             const int c = col0 + nc;
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
-            // stage: row = lane (64 B), 16-byte chunk q at slot q ^ ((lane >> 1) & 3): conflict-free both ways
+            float v[32];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 b0 = __ldg(b4 + 2 * q), b1 = __ldg(b4 + 2 * q + 1);
-              float v0 = __uint_as_float(r[8 * q + 0]) + b0.x, v1 = __uint_as_float(r[8 * q + 1]) + b0.y;
-              float v2 = __uint_as_float(r[8 * q + 2]) + b0.z, v3 = __uint_as_float(r[8 * q + 3]) + b0.w;
-              float v4 = __uint_as_float(r[8 * q + 4]) + b1.x, v5 = __uint_as_float(r[8 * q + 5]) + b1.y;
-              float v6 = __uint_as_float(r[8 * q + 6]) + b1.z, v7 = __uint_as_float(r[8 * q + 7]) + b1.w;
-              if (p.relu) {
-                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
-                v4 = fmaxf(v4, 0.f); v5 = fmaxf(v5, 0.f); v6 = fmaxf(v6, 0.f); v7 = fmaxf(v7, 0.f);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if (p.x3acc) {   // main splits 1, 2 and the correction accumulator, added with RN fp32
+              for (int acc = 1; acc < 4; ++acc) {
+                if (acc < 3 && acc >= n_main) continue;
+                tmem_ld32(taddr + (uint32_t)acc * 128u + nc, r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
               }
-              *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw_st) << 4)) =
-                  make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
             }
-            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = i * 8 + (lane >> 2);
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((cq ^ ((rr >> 1) & 3)) << 4));
-              if (wvalid[i]) *reinterpret_cast<uint4*>(wrow[i] + (int64_t)c * 2 + cq * 16) = val;
+            for (int q = 0; q < 8; ++q) {
+              const float4 bq = __ldg(b4 + q);
+              v[4 * q + 0] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
             }
-            __syncwarp();
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            for (int l = 0; l < p.out_limbs; ++l) {
+              // stage: row = lane (64 B), 16-byte chunk q at slot q ^ ((lane >> 1) & 3): conflict-free both ways
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t w0 = pack_bf16(v[8 * q + 0], v[8 * q + 1]), w1 = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+                const uint32_t w2 = pack_bf16(v[8 * q + 4], v[8 * q + 5]), w3 = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+                *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw_st) << 4)) = make_uint4(w0, w1, w2, w3);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = i * 8 + (lane >> 2);
+                const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((cq ^ ((rr >> 1) & 3)) << 4));
+                if (wvalid[i]) *reinterpret_cast<uint4*>(wrow[i] + ((int64_t)c + (int64_t)l * p.out_ls) * 2 + cq * 16) = val;
+              }
+              __syncwarp();
+              if (l + 1 < p.out_limbs) {     // next limb = residual after removing this limb's bf16 value
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] -= __bfloat162float(__float2bfloat16(v[i]));
+              }
+            }
           }
         }
         for (; nc < p.BN; nc += 16) {
           if (((nc >> 4) & 1) != hsel) continue;
           float v[16];
           tmem_ld16(taddr + nc, v);
+          if (p.x3acc) {
+            for (int acc = 1; acc < 4; ++acc) {
+              if (acc < 3 && acc >= n_main) continue;
+              float w[16];
+              tmem_ld16(taddr + (uint32_t)acc * 128u + nc, w);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += w[i];
+            }
+          }
           const int c = col0 + nc;
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
 #pragma unroll
@@ -507,17 +595,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!valid) continue;
           const int nvalid = p.Cout - c;
           if (p.out_bf16) {
-            uint8_t* dst = orow + (int64_t)c * 2;
-            if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-              uint4 o0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-              uint4 o1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-              reinterpret_cast<uint4*>(dst)[0] = o0;
-              reinterpret_cast<uint4*>(dst)[1] = o1;
-            } else {
-              __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+            for (int l = 0; l < p.out_limbs; ++l) {
+              uint8_t* dst = orow + ((int64_t)c + (int64_t)l * p.out_ls) * 2;
+              if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                uint4 o0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                uint4 o1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                reinterpret_cast<uint4*>(dst)[0] = o0;
+                reinterpret_cast<uint4*>(dst)[1] = o1;
+              } else {
+                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) d[i] = __float2bfloat16(v[i]);
+                for (int i = 0; i < 16; ++i)
+                  if (i < nvalid) d[i] = __float2bfloat16(v[i]);
+              }
+              if (l + 1 < p.out_limbs) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] -= __bfloat162float(__float2bfloat16(v[i]));
+              }
             }
           } else {
             float* d = reinterpret_cast<float*>(orow) + c;
@@ -586,7 +680,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found (no CUDA driver?)"); return KFN_ERR_CUDA; }
   KFN_REQUIRE(g.Cin % 16 == 0, "tensor-core conv needs Cin % 16 == 0");
   KFN_REQUIRE(g.in_cs % 8 == 0, "input channel stride must keep pixels 16-byte aligned");
-  KFN_REQUIRE(CoutP % 16 == 0 && (CoutP <= 256 || CoutP % 256 == 0), "CoutP must be 16..256 (mult of 16) or k*256");
+  KFN_REQUIRE(CoutP % 16 == 0 && (CoutP <= 128 || CoutP % 128 == 0), "CoutP must be 16..128 (mult of 16) or k*128");
   KFN_REQUIRE(g.istride == 1 || (g.istride == 2 && g.IH % 2 == 0 && g.IW % 2 == 0), "stride must be 1 or 2 (even input)");
   KFN_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
               "TMA needs 16-byte aligned global addresses");
@@ -598,7 +692,9 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   memset(plan->blob, 0, sizeof(plan->blob));
 
   const int KC = tc_pick_kc(g.Cin);
-  const int BN = CoutP < 256 ? CoutP : 256;
+  const bool x3 = g.limbs_w > 1;
+  const int bn_cap = x3 ? 128 : 256;                    // bf16x3: four 128-column accumulators fill TMEM
+  const int BN = CoutP < bn_cap ? CoutP : bn_cap;
   const int row_bytes = KC * 2;                       // == swizzle span
   const uint32_t layout_type = (KC == 64) ? 2u : (KC == 32) ? 4u : 6u;   // SWIZZLE_128B / 64B / 32B
   const CUtensorMapSwizzle swz = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -624,7 +720,22 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   p.istride = g.istride; p.in_cs = g.in_cs;
   p.ntaps = g.ntaps;
   for (int t = 0; t < g.ntaps; ++t) { p.dy[t] = g.dy[t]; p.dx[t] = g.dx[t]; }
-  p.kchunks = g.Cin / KC; p.KC = KC; p.BN = BN;
+  // limb terms (bf16x3 error-compensated mode): which A limb multiplies which W limb, largest products last
+  const int limbs_a = g.limbs_a > 1 ? g.limbs_a : 1, limbs_w = g.limbs_w > 1 ? g.limbs_w : 1;
+  p.n_terms = 0;
+  auto term = [&](int la_, int lw_) { p.la[p.n_terms] = la_; p.lw[p.n_terms] = lw_; ++p.n_terms; };
+  if (limbs_a == 3 && limbs_w == 3) { term(0, 2); term(2, 0); term(1, 1); term(0, 1); term(1, 0); term(0, 0); }
+  else if (limbs_a == 1 && limbs_w == 3) { term(0, 2); term(0, 1); term(0, 0); }
+  else if (limbs_a == 1 && limbs_w == 1) { term(0, 0); }
+  else { set_error("unsupported limb combination"); return KFN_ERR_ARG; }
+  p.cpk = g.Cin / KC;
+  p.kchunks = p.n_terms * p.cpk; p.KC = KC; p.BN = BN;
+  p.in_ls = limbs_a > 1 ? g.in_ls : 0;
+  p.w_cin = g.Cin;
+  p.out_limbs = g.limbs_out > 1 ? g.limbs_out : 1;
+  p.out_ls = p.out_limbs > 1 ? g.out_ls : 0;
+  if (p.n_terms > 1) halo = false;
+  p.x3acc = x3 ? 1 : 0;
   p.n_tiles = CoutP / BN;
   const uint32_t sbo16 = (uint32_t)(8 * row_bytes) >> 4;
   p.desc_hi = sbo16 | (1u << 14) | (layout_type << 29);   // bits 32-45 SBO, 46 version=1, 61-63 layout
@@ -675,10 +786,10 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     plan->smem = (size_t)p.epi_stage_off + kEpiStageBytes + 1024;
     boxA[0] = (cuuint32_t)KC; boxA[1] = (cuuint32_t)bw; boxA[2] = 1u; boxA[3] = (cuuint32_t)bh; boxA[4] = (cuuint32_t)bn;
     if (g.istride == 1) {
-      dimA[0] = g.Cin; dimA[1] = g.IW; dimA[2] = 1; dimA[3] = g.IH; dimA[4] = g.N;
+      dimA[0] = (cuuint64_t)(limbs_a - 1) * p.in_ls + g.Cin; dimA[1] = g.IW; dimA[2] = 1; dimA[3] = g.IH; dimA[4] = g.N;
       strA[0] = cs; strA[1] = cs * g.IW; strA[2] = cs * g.IW; strA[3] = cs * g.IW * g.IH;
     } else {
-      dimA[0] = (cuuint64_t)g.in_cs + g.Cin; dimA[1] = g.IW / 2; dimA[2] = 2; dimA[3] = g.IH / 2; dimA[4] = g.N;
+      dimA[0] = (cuuint64_t)g.in_cs + (cuuint64_t)(limbs_a - 1) * p.in_ls + g.Cin; dimA[1] = g.IW / 2; dimA[2] = 2; dimA[3] = g.IH / 2; dimA[4] = g.N;
       strA[0] = cs * 2; strA[1] = cs * g.IW; strA[2] = cs * g.IW * 2; strA[3] = cs * g.IW * g.IH;
     }
   }
@@ -687,8 +798,8 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r)); return KFN_ERR_CUDA; }
   // ---- B: packed weights [tap][CoutP][Cin]
-  cuuint64_t dimB[3] = {(cuuint64_t)g.Cin, (cuuint64_t)CoutP, (cuuint64_t)g.ntaps};
-  cuuint64_t strB[2] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Cin * 2 * CoutP};
+  cuuint64_t dimB[3] = {(cuuint64_t)g.Cin * limbs_w, (cuuint64_t)CoutP, (cuuint64_t)g.ntaps};
+  cuuint64_t strB[2] = {(cuuint64_t)g.Cin * limbs_w * 2, (cuuint64_t)g.Cin * limbs_w * 2 * CoutP};
   cuuint32_t boxB[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1u};
   r = encode(tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dimB, strB, boxB, ones,
              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

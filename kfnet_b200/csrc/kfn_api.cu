@@ -74,7 +74,7 @@ struct Arena {
   }
 };
 
-struct Act { void* p; int N, H, W, C; };   // NHWC view, C = channel stride of the buffer
+struct Act { void* p; int N, H, W, C; int limbs; };   // NHWC view, C = channels per limb of the buffer; limbs 0 = mode default
 
 }  // namespace
 
@@ -89,7 +89,10 @@ struct kfn_handle {
 
 namespace {
 
-int esize(const kfn_handle* h) { return h->mode == KFN_MODE_BF16 ? 2 : 4; }
+// bytes per LOGICAL activation element (allocation) and per STORED element (pointer arithmetic inside a limb)
+int esize(const kfn_handle* h) { return h->mode == KFN_MODE_BF16 ? 2 : h->mode == KFN_MODE_BF16X3 ? 6 : 4; }
+int elem_bytes(const kfn_handle* h) { return h->mode == KFN_MODE_FP32 ? 4 : 2; }
+bool is_tc(const kfn_handle* h) { return h->mode != KFN_MODE_FP32; }
 
 // tap valid iff some m-grid row reads an in-range input pixel through it
 bool tap_live(int d, int M, int stride, int I) {
@@ -137,7 +140,8 @@ int pack_op(kfn_handle* h, const std::string& key, const LayerSpec& L, int phase
   op.ntaps = (int)taps.size();
   if (op.ntaps == 0 || op.ntaps > 9) { set_error("bad tap count for " + key); return KFN_ERR_ARG; }
   for (int t = 0; t < op.ntaps; ++t) { op.dy[t] = taps[t].dy; op.dx[t] = taps[t].dx; }
-  const bool bf16 = h->mode == KFN_MODE_BF16;
+  const bool bf16 = is_tc(h);
+  const int wl = h->mode == KFN_MODE_BF16X3 ? 3 : 1;     // weight limbs
   op.CoutP = bf16 ? tc_cout_padded(L.cout) : (L.cout + 3) / 4 * 4;
 
   // element (tap t, ci, co) of the logical [taps][Cin][Cout] operand
@@ -167,14 +171,21 @@ int pack_op(kfn_handle* h, const std::string& key, const LayerSpec& L, int phase
     h->allocs.push_back(op.w);
     KFN_CUDA_OK(cudaMemcpy(op.w, pk.data(), nelem * sizeof(float), cudaMemcpyHostToDevice));
   } else {
-    std::vector<__nv_bfloat16> pk(nelem, __float2bfloat16(0.f));
+    // [tap][CoutP][limb][Cin]; limb l = bf16 of the residual left by limbs < l
+    std::vector<__nv_bfloat16> pk(nelem * wl, __float2bfloat16(0.f));
     for (int t = 0; t < op.ntaps; ++t)
       for (int co = 0; co < L.cout; ++co)
-        for (int ci = 0; ci < op.Cin; ++ci)
-          pk[((size_t)t * op.CoutP + co) * op.Cin + ci] = __float2bfloat16(W(t, ci, co));
-    KFN_CUDA_OK(cudaMalloc(&op.w, nelem * sizeof(__nv_bfloat16)));
+        for (int ci = 0; ci < op.Cin; ++ci) {
+          float r = W(t, ci, co);
+          for (int l = 0; l < wl; ++l) {
+            const __nv_bfloat16 b = __float2bfloat16(r);
+            pk[(((size_t)t * op.CoutP + co) * wl + l) * op.Cin + ci] = b;
+            r -= __bfloat162float(b);
+          }
+        }
+    KFN_CUDA_OK(cudaMalloc(&op.w, nelem * wl * sizeof(__nv_bfloat16)));
     h->allocs.push_back(op.w);
-    KFN_CUDA_OK(cudaMemcpy(op.w, pk.data(), nelem * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    KFN_CUDA_OK(cudaMemcpy(op.w, pk.data(), nelem * wl * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
   }
   h->ops[key] = op;
   return KFN_OK;
@@ -190,11 +201,15 @@ int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
   ConvGeom g;
   memset(&g, 0, sizeof(g));
   g.N = in.N; g.MH = MH; g.MW = MW;
-  g.IH = in.H; g.IW = in.W; g.in_cs = in.C; g.Cin = op.Cin;
+  const bool x3 = h->mode == KFN_MODE_BF16X3;
+  const int la = x3 ? (in.limbs ? in.limbs : 3) : 1;
+  const int lo = (x3 && !out_fp32) ? 3 : 1;
+  g.IH = in.H; g.IW = in.W; g.in_cs = in.C * la; g.Cin = op.Cin;
+  g.limbs_a = la; g.limbs_w = x3 ? 3 : 1; g.limbs_out = lo; g.in_ls = in.C; g.out_ls = out.C;
   g.istride = op.stride;
   g.ntaps = op.ntaps;
   for (int t = 0; t < op.ntaps; ++t) { g.dy[t] = op.dy[t]; g.dx[t] = op.dx[t]; }
-  g.OH = out.H; g.OW = out.W; g.out_cs = out.C; g.out_coff = out_coff; g.Cout = op.Cout;
+  g.OH = out.H; g.OW = out.W; g.out_cs = out.C * lo; g.out_coff = out_coff; g.Cout = op.Cout;
   g.omul = omul; g.oaddy = oaddy; g.oaddx = oaddx; g.relu = op.relu; g.epi = epi;
   if (h->mode == KFN_MODE_FP32) {
     return launch_conv_simt(g, reinterpret_cast<const float*>(in.p), reinterpret_cast<const float*>(op.w), op.CoutP,
@@ -226,7 +241,7 @@ int deconv(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
   return KFN_OK;
 }
 
-Act act(void* p, int N, int H, int W, int C) { return Act{p, N, H, W, C}; }
+Act act(void* p, int N, int H, int W, int C, int limbs = 0) { return Act{p, N, H, W, C, limbs}; }
 void* offs(void* p, int64_t elems, int es) { return p ? reinterpret_cast<uint8_t*>(p) + elems * es : nullptr; }
 
 // ---------------------------------------------------------------------------------------------
@@ -244,7 +259,7 @@ int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, 
     if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 3), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
   } else {
     if ((rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
-    if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 32), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
+    if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
   }
   struct Step { const char* name; int div; int c; };
   const Step steps[] = {{"conv1b", 1, 64},  {"conv2a", 2, 256}, {"conv2b", 2, 256}, {"conv3a", 4, 512}, {"conv3b", 4, 512},
@@ -274,7 +289,7 @@ int tower_impl(kfn_handle* h, const uint8_t* images, int B, float* feat, Arena& 
     if ((rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 3), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
   } else {
     if ((rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
-    if ((rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 32), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
+    if ((rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
   }
   struct Step { const char* name; int div; int c; };
   const Step steps[] = {{"feat2", 2, 32}, {"feat3", 2, 32}, {"feat4", 4, 64}, {"feat5", 4, 64}, {"feat6", 8, 128}};
@@ -316,15 +331,18 @@ int oflownet_impl(kfn_handle* h, const float* f_prev, const float* f_cur, int NP
   if (dry) return KFN_OK;
   if (ar.overflow) { set_error("workspace too small for oflownet_forward"); return KFN_ERR_WORKSPACE; }
   int rc;
-  if ((rc = launch_diff_volume(f_prev, f_cur, NP, h->GH, h->GW, diff, h->mode == KFN_MODE_BF16, st))) return rc;
+  const int vs = elem_bytes(h);   // bytes per stored element, for channel-offset views
+  if ((rc = launch_diff_volume(f_prev, f_cur, NP, h->GH, h->GW, diff,
+                               h->mode == KFN_MODE_BF16 ? 1 : h->mode == KFN_MODE_BF16X3 ? 3 : 0, st)))
+    return rc;
   const std::string T = "Temporal/";
 #define RUN(x) if ((rc = (x))) return rc
   RUN(conv(h, T + "conv0", act(diff, R, 8, 8, 32), act(cat0, R, 8, 8, 48), 16, EPI_NONE, false, st));
-  RUN(conv(h, T + "conv1a", act(offs(cat0, 16, es), R, 8, 8, 48), act(c1a, R, 4, 4, 32), 0, EPI_NONE, false, st));
+  RUN(conv(h, T + "conv1a", act(offs(cat0, 16, vs), R, 8, 8, 48), act(c1a, R, 4, 4, 32), 0, EPI_NONE, false, st));
   RUN(conv(h, T + "conv1b", act(c1a, R, 4, 4, 32), act(cat1, R, 4, 4, 64), 32, EPI_NONE, false, st));
-  RUN(conv(h, T + "conv2a", act(offs(cat1, 32, es), R, 4, 4, 64), act(c2a, R, 2, 2, 64), 0, EPI_NONE, false, st));
+  RUN(conv(h, T + "conv2a", act(offs(cat1, 32, vs), R, 4, 4, 64), act(c2a, R, 2, 2, 64), 0, EPI_NONE, false, st));
   RUN(conv(h, T + "conv2b", act(c2a, R, 2, 2, 64), act(cat2, R, 2, 2, 128), 64, EPI_NONE, false, st));
-  RUN(conv(h, T + "conv3a", act(offs(cat2, 64, es), R, 2, 2, 128), act(c3a, R, 1, 1, 128), 0, EPI_NONE, false, st));
+  RUN(conv(h, T + "conv3a", act(offs(cat2, 64, vs), R, 2, 2, 128), act(c3a, R, 1, 1, 128), 0, EPI_NONE, false, st));
   RUN(conv(h, T + "conv3b", act(c3a, R, 1, 1, 128), act(c3b, R, 1, 1, 128), 0, EPI_NONE, false, st));
   RUN(deconv(h, T + "upconv2", act(c3b, R, 1, 1, 128), act(cat2, R, 2, 2, 128), 0, st));
   RUN(conv(h, T + "conv4", act(cat2, R, 2, 2, 128), act(c4, R, 2, 2, 64), 0, EPI_NONE, false, st));
@@ -350,7 +368,7 @@ const char* kfn_last_error(void) { return kfn::g_error.c_str(); }
 
 int kfn_create(kfn_handle** out, int device, int mode, int image_h, int image_w) {
   KFN_REQUIRE(out != nullptr, "null out");
-  KFN_REQUIRE(mode == KFN_MODE_FP32 || mode == KFN_MODE_BF16, "unknown mode");
+  KFN_REQUIRE(mode == KFN_MODE_FP32 || mode == KFN_MODE_BF16 || mode == KFN_MODE_BF16X3, "unknown mode");
   KFN_REQUIRE(image_h > 0 && image_w > 0 && image_h % 8 == 0 && image_w % 8 == 0, "image size must be a multiple of 8");
   int ndev = 0;
   KFN_CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -402,7 +420,7 @@ int kfn_finalize_weights(kfn_handle* h) {
   KFN_CUDA_OK(cudaSetDevice(h->device));
   for (void* p : h->allocs) cudaFree(p);
   h->allocs.clear(); h->ops.clear(); h->plans.clear();
-  const bool bf16 = h->mode == KFN_MODE_BF16;
+  const bool bf16 = is_tc(h);
   // spatial dims (output m-grid MH x MW, input IH x IW) of every layer, for tap pruning
   int rc;
   int sh = h->H, sw = h->W;   // running SCoordNet / tower resolution

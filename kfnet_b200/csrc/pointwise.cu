@@ -99,7 +99,7 @@ int launch_l2norm32(float* x, int64_t rows, cudaStream_t st) {
 // in registers, the loop over the remaining offsets is fully unrolled (all neighbour loads in flight at once), and
 // every store instruction of the warp writes one contiguous 512-byte run.  ~15 instructions per 16 bytes stored
 // (the first version decoded (n,p,k,g) per thread with div/mod: ~100 instructions, instruction bound at 45 % of HBM).
-template <bool kBf16>
+template <bool kBf16, int LIMBS>
 __global__ void __launch_bounds__(256) diff_volume_kernel(const float* __restrict__ f_prev, const float* __restrict__ f_cur,
                                                           uint4* __restrict__ out, int64_t npix, int GH, int GW) {
   constexpr int CH = kBf16 ? 8 : 4;            // channels per lane
@@ -133,7 +133,23 @@ __global__ void __launch_bounds__(256) diff_volume_kernel(const float* __restric
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       uint4 o;
-      if constexpr (kBf16) {
+      if constexpr (kBf16 && LIMBS == 3) {
+        // bf16x3: three limbs per (pixel, offset): [limb][32 channels]
+        float d[8] = {a0.x - b0[it].x, a0.y - b0[it].y, a0.z - b0[it].z, a0.w - b0[it].w,
+                      a1.x - b1[it].x, a1.y - b1[it].y, a1.z - b1[it].z, a1.w - b1[it].w};
+        uint4* base = out + ((np * 64 + it * KSUB + ksub) * 3) * GROUPS + g;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(d[0], d[1]), h1 = __floats2bfloat162_rn(d[2], d[3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(d[4], d[5]), h3 = __floats2bfloat162_rn(d[6], d[7]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+          base[l * GROUPS] = o;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] -= __bfloat162float(__float2bfloat16(d[i]));
+        }
+        continue;
+      } else if constexpr (kBf16) {
         __nv_bfloat162 h0 = __floats2bfloat162_rn(a0.x - b0[it].x, a0.y - b0[it].y);
         __nv_bfloat162 h1 = __floats2bfloat162_rn(a0.z - b0[it].z, a0.w - b0[it].w);
         __nv_bfloat162 h2 = __floats2bfloat162_rn(a1.x - b1[it].x, a1.y - b1[it].y);
@@ -154,10 +170,12 @@ int launch_diff_volume(const float* f_prev, const float* f_cur, int NP, int GH, 
   const int64_t npix = (int64_t)NP * GH * GW;     // one warp each
   int64_t blocks = (npix + 7) / 8;
   if (blocks > 148 * 64) blocks = 148 * 64;       // grid-stride beyond that; multiple of the SM count
-  if (out_bf16)
-    diff_volume_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, reinterpret_cast<uint4*>(diff), npix, GH, GW);
+  if (out_bf16 == 3)
+    diff_volume_kernel<true, 3><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, reinterpret_cast<uint4*>(diff), npix, GH, GW);
+  else if (out_bf16)
+    diff_volume_kernel<true, 1><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, reinterpret_cast<uint4*>(diff), npix, GH, GW);
   else
-    diff_volume_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, reinterpret_cast<uint4*>(diff), npix, GH, GW);
+    diff_volume_kernel<false, 1><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, reinterpret_cast<uint4*>(diff), npix, GH, GW);
   KFN_LAUNCH_OK();
   return KFN_OK;
 }

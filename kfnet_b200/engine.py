@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from .synth import weight_shapes
 
-MODES = {"fp32": _lib.KFN_MODE_FP32, "bf16": _lib.KFN_MODE_BF16}
+MODES = {"fp32": _lib.KFN_MODE_FP32, "bf16": _lib.KFN_MODE_BF16, "bf16x3": _lib.KFN_MODE_BF16X3}
 
 
 def _ptr(t):
