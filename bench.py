@@ -234,8 +234,8 @@ def run_ours(args):
     feat = eng.oflow_feat(dev_imgs[0, :ppb + 1])
     t_of = stage_ms(lambda: eng.oflownet(feat[:-1].contiguous(), feat[1:].contiguous()))
     fp_, fc_ = feat[:-1].contiguous(), feat[1:].contiguous()
-    dv_out = eng.diff_volume(fp_, fc_, bf16=(args.mode == "bf16"))
-    t_dv = stage_ms(lambda: eng.diff_volume(fp_, fc_, bf16=(args.mode == "bf16"), out=dv_out), reps=10)
+    dv_out = eng.diff_volume(fp_, fc_, bf16=(args.mode != "fp32"))
+    t_dv = stage_ms(lambda: eng.diff_volume(fp_, fc_, bf16=(args.mode != "fp32"), out=dv_out), reps=10)
     pk = peaks()
     tf_ach = GFLOP_SCOORDNET * B / t_sc            # GFLOP / ms = TFLOP/s
     dv_bytes = ppb * (2 * 60 * 80 * 32 * 4 + 4800 * 64 * 32 * (2 if args.mode == "bf16" else 4))
@@ -248,7 +248,7 @@ def run_ours(args):
         line = {
             "metric": "frames/sec at 480x640 (60x80 label grid)", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (3 bf16 limbs, fp32 accumulate)", "fp32": "f32"}[args.mode], "data": "synthetic",
             "config": {"workload": "full KFNet recurrent eval (SCoordNet + OFlowNet tower/diff-volume/U-Net + warp + Kalman scan), "
                                    "one %d-frame synthetic 480x640 sequence per GPU (BASELINE configs[3]; configs[4] over N GPUs), "
                                    "random weights" % T,
@@ -282,7 +282,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--frames_per_batch", type=int, default=16)
     ap.add_argument("--pairs_per_batch", type=int, default=16)
