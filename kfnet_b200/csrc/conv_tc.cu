@@ -59,6 +59,7 @@ struct __align__(8) TcParams {
   int pf_dist;                  // L2 prefetch distance in tiles (0 = off)
   // bf16x3: k-chunks = n_terms x cpk; term t multiplies A limb la[t] with W limb lw[t]
   int n_terms, cpk, in_ls, w_cin, out_limbs, out_ls;
+  uint32_t tmem_cols, acc_stride;   // TMEM columns allocated by this CTA (power of 2 >= 32) and columns per accumulator stage
   int x3acc;                    // 1: four 128-column TMEM accumulators (3 main-term splits + corrections), single-buffered
   int la[6], lw[6];
   uint32_t epi_stage_off;       // byte offset (from the 1024-aligned smem base) of the epilogue staging area
@@ -210,7 +211,7 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint32_t smem_base, 
     const uint32_t aph = (uint32_t)(j >> 1) & 1u;
     mbar_wait(smem_u32(&s_tempty[a]), aph ^ 1u);
     tc_fence_after();
-    const uint32_t tmem_d = tmem_base + (uint32_t)a * 256u;
+    const uint32_t tmem_d = tmem_base + (uint32_t)a * p.acc_stride;
     for (int kb = 0; kb < kblocks; ++kb) {
       mbar_wait(smem_u32(&s_full[s]), ph);
       tc_fence_after();
@@ -244,7 +245,7 @@ __device__ __forceinline__ void mma_role_halo(const TcParams& p, uint32_t smem_b
     const uint32_t aph = (uint32_t)(j >> 1) & 1u;
     mbar_wait(smem_u32(&s_tempty[a]), aph ^ 1u);
     tc_fence_after();
-    const uint32_t tmem_d = tmem_base + (uint32_t)a * 256u;
+    const uint32_t tmem_d = tmem_base + (uint32_t)a * p.acc_stride;
     uint64_t bchunk = b0;
     for (int kc = 0; kc < p.kchunks; ++kc) {
       mbar_wait(smem_u32(&s_full[s]), ph);
@@ -303,8 +304,7 @@ __device__ __forceinline__ void mma_role_x3(const TcParams& p, uint32_t smem_bas
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+__device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full[kMaxStages];
   __shared__ __align__(8) uint64_t s_empty[kMaxStages];
@@ -336,7 +336,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {   // whole warp: TMEM allocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
-                 "r"(kTmemCols)
+                 "r"(p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -480,7 +480,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aph = p.x3acc ? ((uint32_t)j & 1u) : ((uint32_t)(j >> 1) & 1u);
       mbar_wait(smem_u32(&s_tfull[a]), aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (p.x3acc ? 0u : (uint32_t)a * 256u);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (p.x3acc ? 0u : (uint32_t)a * p.acc_stride);
       const int col0 = it.nt * p.BN;
       const int n_main = p.ntaps < 3 ? p.ntaps : 3;     // x3acc: main-term accumulators in use
 
@@ -636,8 +636,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
+}
+
+// One CTA per SM for the big compute-bound layers; two co-resident CTAs per SM (half the smem budget, TMEM by need)
+// for the small latency-bound ones, so one CTA's barrier / TMA / TMEM latencies are covered by the other's work.
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  conv_tc_body(tmA, tmB, p);
+}
+__global__ void __launch_bounds__(kThreads, 2)
+conv_tc_kernel_x2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  conv_tc_body(tmA, tmB, p);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -665,6 +676,10 @@ int pow2_divisor(int v, int cap) { int d = 1; while (d * 2 <= cap && v % (d * 2)
 
 bool tc_halo_enabled() {
   static const bool on = [] { const char* e = getenv("KFN_TC_HALO"); return !(e && e[0] == '0'); }();
+  return on;
+}
+bool tc_two_ctas_enabled() {
+  static const bool on = [] { const char* e = getenv("KFN_TC_TWO_CTAS"); return !(e && e[0] == '0'); }();
   return on;
 }
 bool tc_prefetch_enabled() {
@@ -714,7 +729,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   }
   const uint32_t w_tile_bytes = ((uint32_t)(BN * row_bytes) + 1023u) & ~1023u;
   const uint32_t w_total = (uint32_t)(g.ntaps * (g.Cin / KC)) * w_tile_bytes;
-  if (halo && w_total > 100 * 1024) halo = false;
+  if (halo && w_total > 100 * 1024) halo = false;   // (two-CTA plans re-check against their smaller budget below)
 
   p.N = g.N; p.MH = g.MH; p.MW = g.MW;
   p.istride = g.istride; p.in_cs = g.in_cs;
@@ -748,7 +763,17 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   p.out = out; p.bias = bias_padded;
   if (g.epi == EPI_L2NORM) KFN_REQUIRE(BN == 32 && g.Cout == 32 && !out_bf16 && g.out_cs % 4 == 0, "l2norm epilogue shape");
 
-  const uint32_t budget = 200 * 1024;
+  // occupancy: 2 CTAs/SM when the accumulators need <= 256 TMEM columns and an 88 KB smem budget still gives the
+  // pipeline its full depth (or the layer is small anyway); big layers keep the whole SM
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)BN) tmem_cols <<= 1;
+  if (x3) tmem_cols = 512;
+  p.tmem_cols = tmem_cols;
+  p.acc_stride = x3 ? 128u : tmem_cols / 2;
+  const uint32_t stage_guess = ((uint32_t)(kBlockM + BN) * row_bytes + 1023u) & ~1023u;
+  const bool two_ctas = tc_two_ctas_enabled() && tmem_cols <= 256 && (12u * stage_guess <= 88u * 1024u || BN <= 64);
+  plan->ctas_per_sm = two_ctas ? 2 : 1;
+  const uint32_t budget = two_ctas ? 88 * 1024 : 200 * 1024;   // 2 x (88 + 16 staging + 1 align + static) KB fits the 228 KB SM
   cuuint64_t dimA[5], strA[4];
   cuuint32_t boxA[5];
   if (halo) {
@@ -760,7 +785,9 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     p.w_tile_bytes = w_tile_bytes; p.w_bytes_total = w_total;
     for (int t = 0; t < g.ntaps; ++t)
       p.tap_off16[t] = (uint32_t)(((1 + g.dy[t]) * 10 * hbn + (1 + g.dx[t])) * row_bytes) >> 4;
-    int stages = (int)((budget - w_total) / p.stage_bytes);
+    uint32_t hb = budget;
+    if (w_total + 3 * p.stage_bytes > hb) { hb = 200 * 1024; plan->ctas_per_sm = 1; }
+    int stages = (int)((hb - w_total) / p.stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     KFN_REQUIRE(stages >= 2, "halo pipeline needs at least 2 stages");
     p.stages = stages;
@@ -815,19 +842,25 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     p.pf_dist = (tc_prefetch_enabled() && (halo || kblocks <= 18)) ? dist : 0;
   }
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
-  plan->grid = total_tiles < num_sms ? total_tiles : num_sms;
+  const int max_ctas = num_sms * plan->ctas_per_sm;
+  plan->grid = total_tiles < max_ctas ? total_tiles : max_ctas;
   return KFN_OK;
 }
 
 int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024 + 1024 + (int)kEpiStageBytes));
+    const int max_smem = 201 * 1024 + 1024 + (int)kEpiStageBytes;
+    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, 106 * 1024));
     attr_set = true;
   }
   const CUtensorMap* tmA = reinterpret_cast<const CUtensorMap*>(plan.blob);
   const TcParams& p = *reinterpret_cast<const TcParams*>(tmA + 2);
-  conv_tc_kernel<<<plan.grid, kThreads, plan.smem, st>>>(tmA[0], tmA[1], p);
+  if (plan.ctas_per_sm == 2)
+    conv_tc_kernel_x2<<<plan.grid, kThreads, plan.smem, st>>>(tmA[0], tmA[1], p);
+  else
+    conv_tc_kernel<<<plan.grid, kThreads, plan.smem, st>>>(tmA[0], tmA[1], p);
   KFN_LAUNCH_OK();
   return KFN_OK;
 }

@@ -8,11 +8,13 @@ namespace kfn {
 struct TcConvPlan {
   alignas(64) uint8_t blob[768];
   int grid;
+  int ctas_per_sm;
   size_t smem;
 };
 
 bool tc_halo_enabled();           // KFN_TC_HALO=0 disables the halo-tile variant (A/B measurements)
 bool tc_prefetch_enabled();       // KFN_TC_PREFETCH=1 enables the producer TMA L2 prefetch (measured: no gain, off by default)
+bool tc_two_ctas_enabled();       // KFN_TC_TWO_CTAS=0: always one CTA per SM (A/B measurements)
 int tc_pick_kc(int Cin);          // channels per k-block: 64 / 32 / 16 (128B / 64B / 32B swizzle)
 int tc_cout_padded(int Cout);     // weights are packed [tap][CoutP][Cin] bf16 with CoutP = roundup(Cout, 16)
 
