@@ -245,20 +245,22 @@ Act act(void* p, int N, int H, int W, int C, int limbs = 0) { return Act{p, N, H
 void* offs(void* p, int64_t elems, int es) { return p ? reinterpret_cast<uint8_t*>(p) + elems * es : nullptr; }
 
 // ---------------------------------------------------------------------------------------------
-int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, Arena& ar, cudaStream_t st, bool dry) {
+// `shared_pre`: optional already-preprocessed input (im2col / fp32) shared with the feature tower by kfn_eval_sequences
+int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, Arena& ar, cudaStream_t st, bool dry,
+                   void* shared_pre = nullptr) {
   const int H = h->H, W = h->W, es = esize(h);
   const int64_t px = (int64_t)B * H * W;
-  void* pre = ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
+  void* pre = shared_pre ? shared_pre : ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
   void* bufA = ar.alloc(px * 64 * es);
   void* bufB = ar.alloc(px * 64 * es);
   if (dry) return KFN_OK;
   if (ar.overflow) { set_error("workspace too small for scoordnet_forward"); return KFN_ERR_WORKSPACE; }
   int rc;
   if (h->mode == KFN_MODE_FP32) {
-    if ((rc = launch_preprocess_f32(images, (float*)pre, px * 3, st))) return rc;
+    if (!shared_pre && (rc = launch_preprocess_f32(images, (float*)pre, px * 3, st))) return rc;
     if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 3), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
   } else {
-    if ((rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
+    if (!shared_pre && (rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
     if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
   }
   struct Step { const char* name; int div; int c; };
@@ -275,20 +277,21 @@ int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, 
   return conv(h, "ScoreNet/prediction", cur, act(measure, B, H / 8, W / 8, 4), 0, EPI_EXP_CH3, true, st);
 }
 
-int tower_impl(kfn_handle* h, const uint8_t* images, int B, float* feat, Arena& ar, cudaStream_t st, bool dry) {
+int tower_impl(kfn_handle* h, const uint8_t* images, int B, float* feat, Arena& ar, cudaStream_t st, bool dry,
+               void* shared_pre = nullptr) {
   const int H = h->H, W = h->W, es = esize(h);
   const int64_t px = (int64_t)B * H * W;
-  void* pre = ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
+  void* pre = shared_pre ? shared_pre : ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
   void* bufA = ar.alloc(px * 16 * es);
   void* bufB = ar.alloc(px * 16 * es);
   if (dry) return KFN_OK;
   if (ar.overflow) { set_error("workspace too small for oflow_feat_forward"); return KFN_ERR_WORKSPACE; }
   int rc;
   if (h->mode == KFN_MODE_FP32) {
-    if ((rc = launch_preprocess_f32(images, (float*)pre, px * 3, st))) return rc;
+    if (!shared_pre && (rc = launch_preprocess_f32(images, (float*)pre, px * 3, st))) return rc;
     if ((rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 3), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
   } else {
-    if ((rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
+    if (!shared_pre && (rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
     if ((rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
   }
   struct Step { const char* name; int div; int c; };
@@ -551,8 +554,17 @@ int kfn_eval_sequences(kfn_handle* h, const uint8_t* images, int S, int T, const
   // 1. measurement system + feature tower: frame-parallel over all S*T frames
   for (int64_t f0 = 0; f0 < F; f0 += frames_per_batch) {
     const int B = (int)((F - f0) < frames_per_batch ? (F - f0) : frames_per_batch);
-    { Arena a(sub, sub_bytes); if ((rc = scoordnet_impl(h, images + f0 * img_bytes, B, measure + f0 * P * 4, a, st, false))) return rc; }
-    { Arena a(sub, sub_bytes); if ((rc = tower_impl(h, images + f0 * img_bytes, B, feat + f0 * P * 32, a, st, false))) return rc; }
+    // both networks start from the same preprocessed input (im2col rows / fp32 image): build it once per batch
+    Arena a(sub, sub_bytes);
+    const int64_t px = (int64_t)B * h->H * h->W;
+    void* pre = a.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
+    if (a.overflow) { set_error("workspace too small for eval_sequences"); return KFN_ERR_WORKSPACE; }
+    if (h->mode == KFN_MODE_FP32) { if ((rc = launch_preprocess_f32(images + f0 * img_bytes, (float*)pre, px * 3, st))) return rc; }
+    else { if ((rc = launch_im2col27_bf16(images + f0 * img_bytes, (__nv_bfloat16*)pre, B, h->H, h->W, st))) return rc; }
+    const int64_t mark = a.off;
+    if ((rc = scoordnet_impl(h, images + f0 * img_bytes, B, measure + f0 * P * 4, a, st, false, pre))) return rc;
+    a.off = mark;
+    if ((rc = tower_impl(h, images + f0 * img_bytes, B, feat + f0 * P * 32, a, st, false, pre))) return rc;
   }
   // 2. process system: pair (f-1, f) for every flat frame f >= 1.  Pairs that straddle two sequences are computed and
   //    ignored (frame 0 of every sequence re-initialises the filter, eval.py:94-101).
