@@ -177,11 +177,32 @@ def run_ours(args):
         if world > 1:
             gather_outputs(out, world)          # the path's single collective: all_gather of the per-rank output maps
 
-    stage = torch.empty_like(dev_imgs)
+    # end-to-end path: pinned host images -> device -> eval -> pinned host maps, every step.  Input copies are
+    # double-buffered on a copy stream (the H2D of step i+1 overlaps the compute of step i, as a caller streaming
+    # sequences would do); each step still performs exactly one H2D of its images and one D2H of its maps.
+    stages = [torch.empty_like(dev_imgs), torch.empty_like(dev_imgs)]
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    free = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_i = [0]
+
+    def issue_h2d(k):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[k])
+            stages[k].copy_(host_imgs, non_blocking=True)
+            ready[k].record(copy_stream)
+
+    for k in range(2):
+        free[k].record()
+    issue_h2d(0)
 
     def step_e2e():
-        stage.copy_(host_imgs, non_blocking=True)
-        run_eval(stage)
+        k = e2e_i[0] & 1
+        e2e_i[0] += 1
+        issue_h2d(k ^ 1)                                  # next step's input, overlapped with this step's compute
+        torch.cuda.current_stream().wait_event(ready[k])
+        run_eval(stages[k])
+        free[k].record()
         host_out.copy_(out, non_blocking=True)
         if world > 1:
             gather_outputs(out, world)
@@ -215,7 +236,7 @@ def run_ours(args):
     launches = eng.launch_count()
     ms = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e = timed(step_e2e, args.steps, max(4, args.warmup))      # >= 4: both staging buffers get their graph captured in warm-up
 
     # per-stage device times on this rank (events on the launching stream), for the roofline of the dominant kernel
     def stage_ms(fn, reps=3):

@@ -1,0 +1,53 @@
+"""GPU test of the reference-facing entry point: kfnet_b200.eval.eval(image_list, label_list, transform_file, snapshot)
+on real files laid out like the reference expects (PNG frames, raw float32 [480,640,4] labels, transform.txt,
+model.ckpt-<step>), checking the saved coord_<idx>.npy maps against the oracle's eval loop."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kfnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_eval_cli_matches_oracle_on_files(tmp_path, weights, capsys):
+    import cv2
+    from kfnet_b200 import eval as ev
+    from kfnet_b200 import synth
+    T = 5
+    imgs = synth.make_sequence(T, seed=4)
+    labels = synth.make_labels(T, seed=5)
+    Tfile = synth.make_transform(2)
+    d_in, d_out, d_model = tmp_path / "in", tmp_path / "out", tmp_path / "model"
+    for d in (d_in, d_out, d_model):
+        d.mkdir()
+    ipaths, lpaths = [], []
+    for t in range(T):
+        ip, lp = d_in / f"frame-{t:06d}.color.png", d_in / f"frame-{t:06d}.label.bin"
+        assert cv2.imwrite(str(ip), np.ascontiguousarray(imgs[t][..., ::-1]))            # RGB -> BGR for imwrite
+        labels[t].astype("<f4").tofile(lp)
+        ipaths.append(str(ip)); lpaths.append(str(lp))
+    (d_in / "image_list.txt").write_text("\n".join(ipaths) + "\n")
+    (d_in / "label_list.txt").write_text("\n".join(lpaths) + "\n")
+    np.savetxt(d_in / "transform.txt", Tfile)
+    synth.save_weights(str(d_model / "model.ckpt-7.npz"), weights)
+    snapshot, step = ev.get_snapshot(str(d_model))
+    assert step == 7
+    dists = ev.eval(str(d_in / "image_list.txt"), str(d_in / "label_list.txt"), str(d_in / "transform.txt"), snapshot,
+                    scene="stairs", output_folder=str(d_out), mode="fp32", chunk=2)
+    printed = capsys.readouterr().out
+    assert "Reinitialize at the begin of a new sequence." in printed and "0, frame 1~0" in printed and "Median dist error" in printed
+    # reference semantics (train.py:67-71, eval.py:94-101): iteration i estimates frame group[1]; i == 0 is the pair [1, 0]
+    Tm = ev.get_transform(str(d_in / "transform.txt"))
+    ref = O.eval_sequence(imgs.astype(np.float32), weights, Tm, seq_len=500, dtype=torch.float64)
+    for t in range(T):
+        got = np.load(d_out / f"coord_{t}.npy")
+        assert got.shape == (60, 80, 4) and got.dtype == np.float32
+        want = ref[t].out_map.numpy()
+        s = np.sqrt((want[..., :3] ** 2).mean())
+        err = np.max(np.abs(got[..., :3] - want[..., :3]) / np.maximum(np.abs(want[..., :3]), s))
+        assert err < 1e-4, (t, err)
+        np.testing.assert_allclose(np.log(got[..., 3]), np.log(want[..., 3]), atol=1e-4)
+    assert len(dists[0]) == T and all(np.isfinite(dists[2]))
