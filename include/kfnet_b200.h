@@ -148,7 +148,7 @@ KFN_API int kfn_eval_sequences(kfn_handle* h, const uint8_t* images, int S, int 
 
 /* One packed layer of the path by name (per-layer parity tests and per-layer roofline measurements).
  *   op_key: "<scope>/<layer>" for conv / dense layers, "<scope>/<layer>#p<k>" (k = 2*py+px) for one sub-pixel phase
- *           of a conv2d_transpose (cnn_wrapper/network.py:116-135, :418-437).
+ *           of a conv2d_transpose, "<scope>/<layer>#all" for all four phases in one GEMM (cnn_wrapper/network.py:116-135, :418-437).
  *   in    : device NHWC [N,IH,IW,in_cs] -- fp32 in KFN_MODE_FP32, bf16 in KFN_MODE_BF16 (the first Cin channels are read;
  *           for the Cin=3 first layers in BF16 mode `in` is the 32-wide im2col buffer)
  *   out   : device NHWC [N,OH,OW,out_cs], channels [out_coff, out_coff+Cout) written; bf16 unless out_fp32 (FP32 mode: always fp32)

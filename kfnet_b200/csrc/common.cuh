@@ -61,6 +61,9 @@ struct ConvGeom {
   // the GEMM accumulates the limb products a1w1 + a1w2 + a2w1 + a2w2 + a1w3 + a3w1 in fp32.
   int limbs_a, limbs_w, limbs_out;
   int in_ls, out_ls;
+  // merged conv2d_transpose: output columns [ph*phase_cout, (ph+1)*phase_cout) belong to sub-pixel phase ph = 2*py+px and
+  // are written to pixel (my*2 + py, mx*2 + px), channels [out_coff, out_coff + phase_cout).  0 = plain layer.
+  int phase_cout;
 };
 enum { EPI_NONE = 0, EPI_EXP_CH3 = 1, EPI_L2NORM = 2 };
 

@@ -127,7 +127,14 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const SimtParams p) {
   for (int i = 0; i < 8; ++i) {
     const int64_t op = s_opix[tm + i];
     if (op < 0) continue;
-    float* dst = p.out + op * g.out_cs + g.out_coff + n0 + tn;
+    int cbase = n0 + tn;
+    int64_t ph_off = 0;
+    if (g.phase_cout) {                     // merged conv2d_transpose phases (4-channel groups never straddle a phase)
+      const int ph = cbase / g.phase_cout;
+      cbase -= ph * g.phase_cout;
+      ph_off = ((int64_t)(ph >> 1) * g.OW + (ph & 1)) * g.out_cs;
+    }
+    float* dst = p.out + op * g.out_cs + ph_off + g.out_coff + cbase;
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -60,6 +60,7 @@ struct __align__(8) TcParams {
   // bf16x3: k-chunks = n_terms x cpk; term t multiplies A limb la[t] with W limb lw[t]
   int n_terms, cpk, in_ls, w_cin, out_limbs, out_ls;
   uint32_t tmem_cols, acc_stride;   // TMEM columns allocated by this CTA (power of 2 >= 32) and columns per accumulator stage
+  int phase_cout;               // merged conv2d_transpose phases (see ConvGeom)
   int x3acc;                    // 1: four 128-column TMEM accumulators (3 main-term splits + corrections), single-buffered
   int la[6], lw[6];
   uint32_t epi_stage_off;       // byte offset (from the 1024-aligned smem base) of the epilogue staging area
@@ -518,12 +519,20 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           bool wvalid[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) { wrow[i] = tile_ptr + wr_off[i]; wvalid[i] = n0 + wr_ni[i] < p.N; }
-          for (; nc + 32 <= p.BN && col0 + nc + 32 <= p.Cout; nc += 32) {
+          for (; nc + 32 <= p.BN && col0 + nc + 32 <= p.Cout && (p.phase_cout == 0 || (p.phase_cout & 31) == 0); nc += 32) {
             if (((nc >> 5) & 1) != hsel) continue;
             uint32_t r[32];
             tmem_ld32(taddr + nc, r);
             const int c = col0 + nc;
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
+            // merged conv2d_transpose: this 32-column block belongs to phase ph -> pixel offset (py, px), channel cc
+            int cc = c;
+            int64_t ph_off = 0;
+            if (p.phase_cout) {
+              const int ph = c / p.phase_cout;
+              cc = c - ph * p.phase_cout;
+              ph_off = ((int64_t)(ph >> 1) * p.OW + (ph & 1)) * p.out_cs * 2;
+            }
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -557,7 +566,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
               for (int i = 0; i < 4; ++i) {
                 const int rr = i * 8 + (lane >> 2);
                 const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((cq ^ ((rr >> 1) & 3)) << 4));
-                if (wvalid[i]) *reinterpret_cast<uint4*>(wrow[i] + ((int64_t)c + (int64_t)l * p.out_ls) * 2 + cq * 16) = val;
+                if (wvalid[i]) *reinterpret_cast<uint4*>(wrow[i] + ph_off + ((int64_t)cc + (int64_t)l * p.out_ls) * 2 + cq * 16) = val;
               }
               __syncwarp();
               if (l + 1 < p.out_limbs) {     // next limb = residual after removing this limb's bf16 value
@@ -594,9 +603,16 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           if (p.epi == EPI_EXP_CH3 && c == 0) v[3] = expf(v[3]);
           if (!valid) continue;
           const int nvalid = p.Cout - c;
+          int cc = c;
+          int64_t ph_off = 0;
+          if (p.phase_cout) {
+            const int ph = c / p.phase_cout;
+            cc = c - ph * p.phase_cout;
+            ph_off = ((int64_t)(ph >> 1) * p.OW + (ph & 1)) * p.out_cs * esize;
+          }
           if (p.out_bf16) {
             for (int l = 0; l < p.out_limbs; ++l) {
-              uint8_t* dst = orow + ((int64_t)c + (int64_t)l * p.out_ls) * 2;
+              uint8_t* dst = orow + ph_off + ((int64_t)cc + (int64_t)l * p.out_ls) * 2;
               if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                 uint4 o0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                 uint4 o1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
@@ -614,7 +630,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
               }
             }
           } else {
-            float* d = reinterpret_cast<float*>(orow) + c;
+            float* d = reinterpret_cast<float*>(orow + ph_off) + cc;
             if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
@@ -751,6 +767,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   p.out_ls = p.out_limbs > 1 ? g.out_ls : 0;
   if (p.n_terms > 1) halo = false;
   p.x3acc = x3 ? 1 : 0;
+  p.phase_cout = g.phase_cout;
   p.n_tiles = CoutP / BN;
   const uint32_t sbo16 = (uint32_t)(8 * row_bytes) >> 4;
   p.desc_hi = sbo16 | (1u << 14) | (layout_type << 29);   // bits 32-45 SBO, 46 version=1, 61-63 layout
@@ -771,7 +788,8 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   p.tmem_cols = tmem_cols;
   p.acc_stride = x3 ? 128u : tmem_cols / 2;
   const uint32_t stage_guess = ((uint32_t)(kBlockM + BN) * row_bytes + 1023u) & ~1023u;
-  const bool two_ctas = tc_two_ctas_enabled() && tmem_cols <= 256 && (12u * stage_guess <= 88u * 1024u || BN <= 64);
+  const bool streaming = g.ntaps == 1 && g.Cin / KC == 1 && (int64_t)g.N * g.MH * g.MW > (1 << 20);   // K=KC 1-tap GEMMs over big maps
+  const bool two_ctas = tc_two_ctas_enabled() && !streaming && tmem_cols <= 256 && (12u * stage_guess <= 88u * 1024u || BN <= 64);
   plan->ctas_per_sm = two_ctas ? 2 : 1;
   const uint32_t budget = two_ctas ? 88 * 1024 : 200 * 1024;   // 2 x (88 + 16 staging + 1 align + static) KB fits the 228 KB SM
   cuuint64_t dimA[5], strA[4];

@@ -60,6 +60,7 @@ struct PackedOp {
   int Cin = 0, Cout = 0, CoutP = 0;
   int ntaps = 0, dy[9] = {0}, dx[9] = {0};
   int stride = 1, relu = 0;
+  int phase_cout = 0;      // merged conv2d_transpose: Cout per phase (op.Cout = 4 * phase_cout)
 };
 
 struct Arena {
@@ -128,6 +129,13 @@ int pack_op(kfn_handle* h, const std::string& key, const LayerSpec& L, int phase
       for (int kx = 0; kx < 3; ++kx)
         if (tap_live(ky - pad, MH, L.stride, IH) && tap_live(kx - pad, MW, L.stride, IW))
           taps.push_back({ky, kx, ky - pad, kx - pad});
+  } else if (phase == 4) {   // DECONV, all four sub-pixel phases in one GEMM: taps (dy,dx) in {0,-1}^2, N = 4*Cout
+    op.Cin = L.cin;
+    op.Cout = 4 * L.cout;
+    op.phase_cout = L.cout;
+    for (int a = 0; a < 2; ++a)
+      for (int c = 0; c < 2; ++c)
+        if (tap_live(-a, MH, 1, IH) && tap_live(-c, MW, 1, IW)) taps.push_back({0, 0, -a, -c});
   } else {   // DECONV phase
     op.Cin = L.cin;
     const int py = phase >> 1, px = phase & 1;
@@ -142,7 +150,7 @@ int pack_op(kfn_handle* h, const std::string& key, const LayerSpec& L, int phase
   for (int t = 0; t < op.ntaps; ++t) { op.dy[t] = taps[t].dy; op.dx[t] = taps[t].dx; }
   const bool bf16 = is_tc(h);
   const int wl = h->mode == KFN_MODE_BF16X3 ? 3 : 1;     // weight limbs
-  op.CoutP = bf16 ? tc_cout_padded(L.cout) : (L.cout + 3) / 4 * 4;
+  op.CoutP = bf16 ? tc_cout_padded(op.Cout) : (op.Cout + 3) / 4 * 4;
 
   // element (tap t, ci, co) of the logical [taps][Cin][Cout] operand
   auto W = [&](int t, int ci, int co) -> float {
@@ -154,11 +162,18 @@ int pack_op(kfn_handle* h, const std::string& key, const LayerSpec& L, int phase
     }
     if (L.kind == DENSE) return w[ci * L.cout + co];
     if (L.kind == CONV) return w[((tp.ky * L.k + tp.kx) * L.cin + ci) * L.cout + co];
+    if (op.phase_cout) {                                           // merged phases (App. A.3: 2i + k = j)
+      const int ph = co / L.cout, ch = co % L.cout, py = ph >> 1, px = ph & 1;
+      const int ky = py ? (tp.dy == 0 ? 1 : -1) : (tp.dy == 0 ? 0 : 2);
+      const int kx = px ? (tp.dx == 0 ? 1 : -1) : (tp.dx == 0 ? 0 : 2);
+      if (ky < 0 || kx < 0) return 0.f;
+      return w[((ky * 3 + kx) * L.cout + ch) * L.cin + ci];
+    }
     return w[((tp.ky * 3 + tp.kx) * L.cout + co) * L.cin + ci];   // DECONV [kh,kw,Cout,Cin]
   };
   const size_t nelem = (size_t)op.ntaps * op.Cin * op.CoutP;
   std::vector<float> biasp(op.CoutP, 0.f);
-  for (int co = 0; co < L.cout; ++co) biasp[co] = b[co];
+  for (int co = 0; co < op.Cout; ++co) biasp[co] = b[co % L.cout];
   KFN_CUDA_OK(cudaMalloc(&op.bias, op.CoutP * sizeof(float)));
   h->allocs.push_back(op.bias);
   KFN_CUDA_OK(cudaMemcpy(op.bias, biasp.data(), op.CoutP * sizeof(float), cudaMemcpyHostToDevice));
@@ -166,7 +181,7 @@ int pack_op(kfn_handle* h, const std::string& key, const LayerSpec& L, int phase
     std::vector<float> pk(nelem, 0.f);
     for (int t = 0; t < op.ntaps; ++t)
       for (int ci = 0; ci < op.Cin; ++ci)
-        for (int co = 0; co < L.cout; ++co) pk[((size_t)t * op.Cin + ci) * op.CoutP + co] = W(t, ci, co);
+        for (int co = 0; co < op.Cout; ++co) pk[((size_t)t * op.Cin + ci) * op.CoutP + co] = W(t, ci, co);
     KFN_CUDA_OK(cudaMalloc(&op.w, nelem * sizeof(float)));
     h->allocs.push_back(op.w);
     KFN_CUDA_OK(cudaMemcpy(op.w, pk.data(), nelem * sizeof(float), cudaMemcpyHostToDevice));
@@ -174,7 +189,7 @@ int pack_op(kfn_handle* h, const std::string& key, const LayerSpec& L, int phase
     // [tap][CoutP][limb][Cin]; limb l = bf16 of the residual left by limbs < l
     std::vector<__nv_bfloat16> pk(nelem * wl, __float2bfloat16(0.f));
     for (int t = 0; t < op.ntaps; ++t)
-      for (int co = 0; co < L.cout; ++co)
+      for (int co = 0; co < op.Cout; ++co)
         for (int ci = 0; ci < op.Cin; ++ci) {
           float r = W(t, ci, co);
           for (int l = 0; l < wl; ++l) {
@@ -211,6 +226,7 @@ int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
   for (int t = 0; t < op.ntaps; ++t) { g.dy[t] = op.dy[t]; g.dx[t] = op.dx[t]; }
   g.OH = out.H; g.OW = out.W; g.out_cs = out.C * lo; g.out_coff = out_coff; g.Cout = op.Cout;
   g.omul = omul; g.oaddy = oaddy; g.oaddx = oaddx; g.relu = op.relu; g.epi = epi;
+  g.phase_cout = op.phase_cout;
   if (h->mode == KFN_MODE_FP32) {
     return launch_conv_simt(g, reinterpret_cast<const float*>(in.p), reinterpret_cast<const float*>(op.w), op.CoutP,
                             op.bias, reinterpret_cast<float*>(out.p), st);
@@ -231,14 +247,10 @@ int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
 int conv(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff, int epi, bool out_fp32, cudaStream_t st) {
   return run_op(h, key, in, out, out_coff, out.H, out.W, 1, 0, 0, epi, out_fp32, st);
 }
-// conv2d_transpose k3 s2 SAME = 4 sub-pixel phase convs over the input grid
+// conv2d_transpose k3 s2 SAME = 4 sub-pixel phase convs over the input grid, run as ONE GEMM with N = 4*Cout
+// (the per-phase ops "<key>#p<k>" stay available through kfn_conv_layer)
 int deconv(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff, cudaStream_t st) {
-  for (int ph = 0; ph < 4; ++ph) {
-    int rc = run_op(h, key + "#p" + std::to_string(ph), in, out, out_coff, in.H, in.W, 2, ph >> 1, ph & 1, EPI_NONE,
-                    false, st);
-    if (rc != KFN_OK) return rc;
-  }
-  return KFN_OK;
+  return run_op(h, key + "#all", in, out, out_coff, in.H, in.W, 2, 0, 0, EPI_NONE, false, st);
 }
 
 Act act(void* p, int N, int H, int W, int C, int limbs = 0) { return Act{p, N, H, W, C, limbs}; }
@@ -455,6 +467,7 @@ int kfn_finalize_weights(kfn_handle* h) {
     if (L.kind == DECONV) {
       for (int ph = 0; ph < 4; ++ph)
         if ((rc = pack_op(h, key + "#p" + std::to_string(ph), L, ph, false, oh, oh, ih, ih))) return rc;
+      if ((rc = pack_op(h, key + "#all", L, 4, false, oh, oh, ih, ih))) return rc;
     } else {
       if ((rc = pack_op(h, key, L, 0, false, oh, oh, ih, ih))) return rc;
     }
@@ -588,6 +601,10 @@ int kfn_conv_layer(kfn_handle* h, const char* op_key, const void* in, int N, int
   const std::string key(op_key);
   Act a = act(const_cast<void*>(in), N, IH, IW, in_cs);
   Act o = act(out, N, OH, OW, out_cs);
+  if (key.size() > 4 && key.compare(key.size() - 4, 4, "#all") == 0) {   // merged conv2d_transpose (all four phases)
+    KFN_REQUIRE(OH == 2 * IH && OW == 2 * IW, "bad conv2d_transpose shape");
+    return run_op(h, key, a, o, out_coff, IH, IW, 2, 0, 0, epi, out_fp32 != 0, (cudaStream_t)stream);
+  }
   const size_t hash = key.find("#p");
   if (hash != std::string::npos) {
     const int ph = key[hash + 2] - '0';

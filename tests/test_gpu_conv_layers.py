@@ -95,6 +95,12 @@ def test_deconv_phases_and_concat_offset(engines, weights, mode, spec):
         eng.conv_layer(f"{key}#p{ph}", x.contiguous(), (2 * n, 2 * n), ctot, out_coff=0, out=out)
     assert_close_rms(out[..., :cout].float(), ref, 1e-2 if mode == "bf16" else 2e-5, key)
     assert bool((out[..., cout:] == 7.0).all()), "channels outside [0,Cout) must be untouched"
+    # the same conv2d_transpose as ONE GEMM (N = 4*Cout, epilogue scatters column blocks to the phase positions),
+    # written at a channel offset of a wider buffer
+    out2 = torch.full((N, 2 * n, 2 * n, ctot), 7.0, dtype=x.dtype, device="cuda")
+    eng.conv_layer(f"{key}#all", x.contiguous(), (2 * n, 2 * n), ctot, out_coff=16, out=out2)
+    assert_close_rms(out2[..., 16:16 + cout].float(), ref, 1e-2 if mode == "bf16" else 2e-5, key + " merged phases")
+    assert bool((out2[..., :16] == 7.0).all()) and bool((out2[..., 16 + cout:] == 7.0).all())
 
 
 def test_first_layer_im2col_weights(engines, weights):
