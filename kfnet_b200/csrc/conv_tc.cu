@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
@@ -317,6 +318,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // programmatic dependent launch: let the next kernel's CTAs be scheduled as SMs free up (they run their own
+  // prologue and then block in griddepcontrol.wait until this grid has completed and flushed)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -345,6 +349,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // from here on we touch global memory, so wait for the previous grid (no-op without the PDL launch attribute)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles;
@@ -698,6 +705,10 @@ bool tc_two_ctas_enabled() {
   static const bool on = [] { const char* e = getenv("KFN_TC_TWO_CTAS"); return !(e && e[0] == '0'); }();
   return on;
 }
+bool tc_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("KFN_TC_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 bool tc_prefetch_enabled() {
   static const bool on = [] { const char* e = getenv("KFN_TC_PREFETCH"); return e && e[0] == '1'; }();
   return on;
@@ -875,10 +886,21 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
   }
   const CUtensorMap* tmA = reinterpret_cast<const CUtensorMap*>(plan.blob);
   const TcParams& p = *reinterpret_cast<const TcParams*>(tmA + 2);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)plan.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
   if (plan.ctas_per_sm == 2)
-    conv_tc_kernel_x2<<<plan.grid, kThreads, plan.smem, st>>>(tmA[0], tmA[1], p);
+    KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_x2, tmA[0], tmA[1], p));
   else
-    conv_tc_kernel<<<plan.grid, kThreads, plan.smem, st>>>(tmA[0], tmA[1], p);
+    KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel, tmA[0], tmA[1], p));
   KFN_LAUNCH_OK();
   return KFN_OK;
 }
