@@ -108,15 +108,19 @@ def coord_loss_with_uncertainty(pred, unc, gt, mask, transform, dist_threshold=0
 
 
 def load_snapshot_weights(snapshot):
+    """`snapshot` = `<model_folder>/model.ckpt-<step>` as returned by get_snapshot.  Accepts this package's `.npz`
+    container (TF variable names, TF layouts) or a TensorFlow checkpoint-V2 (`.index` + `.data-*`, tf_checkpoint.py)."""
     from . import synth
     if snapshot is None:
         raise FileNotFoundError("no model.ckpt-* snapshot found")
     if os.path.exists(snapshot + ".npz"):
         return synth.load_weights(snapshot + ".npz")
+    if os.path.exists(snapshot + ".index"):
+        from .tf_checkpoint import load_kfnet_weights
+        return load_kfnet_weights(snapshot)                 # scopes 'ScoreNet' + 'Temporal' (eval.py:66-68)
     if os.path.exists(snapshot):
         return synth.load_weights(snapshot)
-    raise NotImplementedError("TensorFlow checkpoint-V2 reading is not implemented (SURVEY 8f N2); convert the "
-                              "variables of scopes 'ScoreNet' and 'Temporal' to model.ckpt-<step>.npz")
+    raise FileNotFoundError("snapshot %s(.npz|.index) not found" % snapshot)
 
 
 def eval(image_list, label_list, transform_file, snapshot, scene="stairs", output_folder="", NIS=False,  # noqa: A001
