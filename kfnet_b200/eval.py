@@ -143,12 +143,26 @@ def eval(image_list, label_list, transform_file, snapshot, scene="stairs", outpu
     state = None
     dists = [[], [], []]
     feat_cache = {}
-    for i0 in range(0, n_iter, chunk):
+    # input pipeline (reference: 1-thread TF queue runner, train.py:203-239): PNG decode / label reads of chunk k+1 run
+    # on a thread pool while the GPU evaluates chunk k (cv2 and numpy file reads release the GIL)
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=max(2, min(16, (os.cpu_count() or 4))))
+
+    def plan(i0):
         its = list(range(i0, min(i0 + chunk, n_iter)))
         pairs = [groups[i % len(groups)] for i in its]
         frames = sorted({f for p in pairs for f in p})
+        futs_i = [pool.submit(load_image, image_paths[f]) for f in frames]
+        futs_l = [pool.submit(load_label, label_paths[p[1]], spec.image_size) for p in pairs]
+        return its, pairs, frames, futs_i, futs_l
+
+    starts = list(range(0, n_iter, chunk))
+    nxt = plan(starts[0]) if starts else None
+    for ci, i0 in enumerate(starts):
+        its, pairs, frames, futs_i, futs_l = nxt
+        nxt = plan(starts[ci + 1]) if ci + 1 < len(starts) else None
         pos = {f: k for k, f in enumerate(frames)}
-        imgs = torch.from_numpy(np.stack([load_image(image_paths[f]) for f in frames])).to(dev)
+        imgs = torch.from_numpy(np.stack([f.result() for f in futs_i])).to(dev)
         measure_all = engine.scoordnet(imgs)                                               # [F,GH,GW,4]
         feat_all = engine.oflow_feat(imgs)
         prev_idx = torch.tensor([pos[p[0]] for p in pairs], device=dev)
@@ -162,7 +176,7 @@ def eval(image_list, label_list, transform_file, snapshot, scene="stairs", outpu
         meas_np = measure[0].cpu().numpy()
         for k, i in enumerate(its):
             prev, index = pairs[k]
-            lab = load_label(label_paths[index], spec.image_size)[::8, ::8]                # nearest-neighbour /8 (train.py:259-261)
+            lab = futs_l[k].result()[::8, ::8]                                             # nearest-neighbour /8 (train.py:259-261)
             gt, mask = lab[..., :3], lab[..., 3:4]
             reinit = (i % spec.sequence_length == 0)
             R, tr = transform[:3, :3], transform[:3, 3]
@@ -184,6 +198,7 @@ def eval(image_list, label_list, transform_file, snapshot, scene="stairs", outpu
                       % (i, prev, index, l_m, l_t, l_k, a_m, a_t, a_k, d_m, d_t, d_kf, get_NIS_measurement(nis[k])))
             if output_folder and os.path.isdir(output_folder):                             # eval.py:122-126
                 np.save(os.path.join(output_folder, "coord_" + str(index) + ".npy"), out_map[k].astype(np.float32))
+    pool.shutdown(wait=False)
     if not quiet:
         print("Median dist error: ", *[np.median(d) for d in dists])
         print("Mean dist error: ", *[np.mean(d) for d in dists])
