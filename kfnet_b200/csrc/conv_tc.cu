@@ -1,4 +1,4 @@
-// tcgen05 / TMA implicit-GEMM convolution for sm_100a (KFN_MODE_BF16).
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (KFN_MODE_BF16 and KFN_MODE_BF16X3).
 //
 // GEMM view of one conv (ConvGeom, common.cuh):  D[M, Cout] = sum_{tap, c} A_tap[M, c] * W[tap][Cout][c]
 //   M tile  = 128 m-grid rows = a (bw x bh x bn) box of pixels, bw*bh*bn = 128, chosen per layer on the host;
@@ -6,14 +6,16 @@
 //             starting at the tap-shifted pixel; out-of-range coordinates are zero-filled by TMA, which IS the
 //             SAME padding of the reference's tf.layers.conv2d.  Stride-2 convs read a
 //             parity-split 5-D view (c|wpar, w/2, hpar, h/2, n) of the same buffer, so no element strides are needed;
-//   B tiles = [BN x KC] K-major slices of the packed weights [tap][CoutP][Cin];
+//             in HALO mode the tile's haloed block is loaded once and the taps are shifted-descriptor MMAs (TcParams);
+//   B tiles = [BN x KC] K-major slices of the packed weights [tap][CoutP][Cin] (resident in smem in halo mode);
 //   both land in shared memory in the canonical K-major swizzled layout (128B/64B/32B for KC = 64/32/16 bf16)
 //   that tcgen05.mma consumes through shared-memory descriptors;
-//   accumulators live in TMEM (2 stages x 256 fp32 columns), drained by 4 epilogue warps with tcgen05.ld
-//   while the next tile's MMAs run; bias + ReLU (+ exp / l2-normalise) fused into the epilogue.
+//   accumulators live in TMEM (2 stages, allocated by need), drained by 8 epilogue warps with tcgen05.ld while the
+//   next tile's MMAs run; bias + ReLU (+ exp / l2-normalise / limb split / conv2d_transpose phase scatter) fused.
 //
-// One persistent CTA per SM (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; the two warps of a quadrant split the columns).
+// One persistent CTA (or two co-resident ones for small layers) per SM, 320 threads: warp 0 = TMA producer,
+// warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; the two warps of a
+// quadrant split the column blocks).  DESIGN.md section 4.1 has the measurements behind each design choice.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -31,7 +33,6 @@ constexpr int kBlockM = 128;
 constexpr int kMaxStages = 12;
 constexpr int kThreads = 320;                           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kEpiWarps = 8;
-constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kEpiStageBytes = kEpiWarps * 2048;     // per epilogue warp: 32 rows x 64 B staging for coalesced stores
 constexpr long long kWatchdogCycles = 4000000000ll;   // ~2 s at 1.9 GHz: trap instead of hanging the GPU
 
@@ -152,15 +153,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
       "tcgen05.wait::ld.sync.aligned;"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
       : "r"(taddr)
       : "memory");
 }

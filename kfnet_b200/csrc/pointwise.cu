@@ -257,6 +257,7 @@ kalman_scan_kernel(const float4* __restrict__ measure, const float2* __restrict_
   __syncthreads();
   const float xmax = (float)(GW - 1), ymax = (float)(GH - 1);
   const float minvar = 1e-5f * 1e-5f;          // KFNet.py:71,396,398 (min_uncertainty^2)
+  const bool need_nis = (nis != nullptr) || (nis_gate != 0);   // the NIS divisions are skipped when nobody reads them
   for (int t = 0; t < T; ++t) {
     const int64_t fr = seq + (int64_t)t * P;
     const int idx = first_index + t;
@@ -297,11 +298,13 @@ kalman_scan_kernel(const float4* __restrict__ measure, const float2* __restrict_
         xp.y = omk * xm.y + K * z.y;
         xp.z = omk * xm.z + K * z.z;
         xp.w = sqrtf(omk * lv);
-        // GetNIS (KFNet.py:164-184): inno_variance = square(sqrt(temp_var + measure_var))
-        const float iu = sqrtf(lv + mv);
-        const float iv = iu * iu;
-        const float d0 = z.x - xm.x, d1 = z.y - xm.y, d2 = z.z - xm.z;
-        n0 = (d0 * d0) / iv; n1 = (d1 * d1) / iv; n2 = (d2 * d2) / iv;
+        if (need_nis) {
+          // GetNIS (KFNet.py:164-184): inno_variance = square(sqrt(temp_var + measure_var))
+          const float iu = sqrtf(lv + mv);
+          const float iv = iu * iu;
+          const float d0 = z.x - xm.x, d1 = z.y - xm.y, d2 = z.z - xm.z;
+          n0 = (d0 * d0) / iv; n1 = (d1 * d1) / iv; n2 = (d2 * d2) / iv;
+        }
         tp = make_int2((int)x0, (int)y0);
       }
       nxt[p] = xp;
