@@ -136,6 +136,11 @@ KFN_API int kfn_flow_warp_kalman(const float* flow, const float* sigma_w, const 
                          const float* transform, int GH, int GW, float* temp, float* kf, float* nis,
                          float* out_map, int32_t* taps, void* stream);
 
+/* Pointwise Kalman update and NIS on already-aligned maps (no warp): KFNet.BuildKFCoord (KFNet.py:148-162) and
+ * KFNet.GetNIS (:164-184).  prior = (last/temp coord xyz, uncertainty), measure = (measure coord xyz, sigma_z):
+ * device fp32 [npix,4]; posterior [npix,4] and/or nis [npix,3] (either may be NULL). */
+KFN_API int kfn_kalman_update(const float* prior, const float* measure, int64_t npix, float* posterior, float* nis, void* stream);
+
 /* Whole eval path for S sequences of T frames resident on the device (the batched, time-decoupled form of the
  * eval.py loop: all conv work frame-parallel, then the scan).  images: device uint8 [S,T,H,W,3];
  * out_map: device fp32 [S,T,GH,GW,4].  frames_per_batch / pairs_per_batch bound the workspace (see

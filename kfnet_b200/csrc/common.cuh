@@ -83,5 +83,6 @@ int launch_kalman_scan(const float* measure, const float* flow, const float* sig
                        float* state_out, const float* T16_host, int S, int T, int GH, int GW, int first_index,
                        int reinit_period, int nis_gate, float* out_map, float* temp, float* kf, float* nis,
                        int32_t* taps, cudaStream_t st);
+int launch_kalman_update(const float* prior, const float* meas, int64_t npix, float* post, float* nis, cudaStream_t st);
 
 }  // namespace kfn

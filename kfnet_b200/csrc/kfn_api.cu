@@ -539,6 +539,11 @@ int kfn_flow_warp_kalman(const float* flow, const float* sigma_w, const float* l
                             nis, taps, (cudaStream_t)stream);
 }
 
+int kfn_kalman_update(const float* prior, const float* measure, int64_t npix, float* posterior, float* nis, void* stream) {
+  KFN_REQUIRE(prior && measure && npix > 0 && (posterior || nis), "null/empty argument");
+  return launch_kalman_update(prior, measure, npix, posterior, nis, (cudaStream_t)stream);
+}
+
 int64_t kfn_sequence_extra_bytes(kfn_handle* h, int S, int T) {
   if (!h || S <= 0 || T <= 0) return KFN_ERR_ARG;
   const int64_t F = (int64_t)S * T, P = (int64_t)h->GH * h->GW;

@@ -353,4 +353,33 @@ int launch_kalman_scan(const float* measure, const float* flow, const float* sig
   return KFN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pointwise Kalman update + NIS without the warp (KFNet.BuildKFCoord, KFNet/KFNet.py:148-162; KFNet.GetNIS, :164-184):
+// prior (x-, sigma-) and measurement (z, sigma_z) as [npix,4] maps -> posterior [npix,4] and NIS [npix,3].
+__global__ void kalman_update_kernel(const float4* __restrict__ prior, const float4* __restrict__ meas, int64_t npix,
+                                     float4* __restrict__ post, float* __restrict__ nis) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const float4 xm = prior[i], z = meas[i];
+  const float lv = xm.w * xm.w, mv = z.w * z.w;
+  if (post) {
+    const float K = lv / (lv + mv);
+    const float omk = fmaxf(1.0f - K, 0.0f);
+    post[i] = make_float4(omk * xm.x + K * z.x, omk * xm.y + K * z.y, omk * xm.z + K * z.z, sqrtf(omk * lv));
+  }
+  if (nis) {
+    const float iu = sqrtf(lv + mv);
+    const float iv = iu * iu;
+    const float d0 = z.x - xm.x, d1 = z.y - xm.y, d2 = z.z - xm.z;
+    nis[i * 3 + 0] = (d0 * d0) / iv; nis[i * 3 + 1] = (d1 * d1) / iv; nis[i * 3 + 2] = (d2 * d2) / iv;
+  }
+}
+
+int launch_kalman_update(const float* prior, const float* meas, int64_t npix, float* post, float* nis, cudaStream_t st) {
+  kalman_update_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const float4*>(prior), reinterpret_cast<const float4*>(meas), npix, reinterpret_cast<float4*>(post), nis);
+  KFN_LAUNCH_OK();
+  return KFN_OK;
+}
+
 }  // namespace kfn

@@ -169,6 +169,15 @@ class Engine:
         res = dict(out_map=out, temp=temp, kf=kf, nis=nis, taps=taps, state=state_out)
         return res
 
+    # ---- pointwise Kalman update / NIS on aligned maps (BuildKFCoord / GetNIS) ----
+    def kalman_update(self, prior, measure, want_nis=False):
+        assert prior.shape == measure.shape and prior.shape[-1] == 4 and prior.is_contiguous() and measure.is_contiguous()
+        npix = prior.numel() // 4
+        post = torch.empty_like(prior)
+        nis = torch.empty(*prior.shape[:-1], 3, dtype=torch.float32, device=prior.device) if want_nis else None
+        _lib.check(self.lib.kfn_kalman_update(_ptr(prior), _ptr(measure), npix, _ptr(post), _ptr(nis), self._stream()))
+        return post, nis
+
     # ---- whole batched eval path on device-resident sequences ----
     def eval_sequences(self, images, transform, reinit_period=500, nis_gate=False, frames_per_batch=8, pairs_per_batch=4,
                        out=None):

@@ -123,6 +123,40 @@ def load_snapshot_weights(snapshot):
     raise FileNotFoundError("snapshot %s(.npz|.index) not found" % snapshot)
 
 
+def KF_fusion(image_list, label_list, transform, last_coord, last_uncertainty, spec, index=0, engine=None, weights=None,
+              mode="fp32"):
+    """Eager counterpart of KFNet/train.py:241-266.  The reference builds this graph once and every `sess.run` pops the
+    next pair of the eval stream off a queue; here `index` selects the iteration.  Returns the same 16-tuple:
+    (measure_coord, measure_uncertainty, temp_coord, temp_uncertainty, KF_coord, KF_uncertainty, NIS, group_indexes,
+     measure_loss, measure_accuracy, temp_loss, temp_accuracy, KF_loss, KF_accuracy, gt_coords_8, masks_8)
+    with torch CUDA tensors for the maps ([1,60,80,C]) and python floats for the scalars.  `transform` is the inverted 4x4."""
+    import torch
+    from .engine import Engine
+    from .kfnet import KFNet
+    image_paths, label_paths = read_lines(image_list), read_lines(label_list)
+    groups = get_indexes(spec.scene)
+    group = groups[index % len(groups)]
+    if engine is None:
+        engine = Engine(weights, mode=mode, image_size=spec.image_size)
+    images = torch.from_numpy(np.stack([load_image(image_paths[f]) for f in group]))
+    spec2 = KFNetDataSpec(batch_size=2, image_size=spec.image_size, scene=spec.scene)
+    net = KFNet(images, spec2, False, False, engine=engine)
+    measure_coord, measure_uncertainty = net.GetMeasureCoord2()
+    temp_coord, temp_uncertainty, KF_coord, KF_uncertainty = net.GetKFCoordRecursive(last_coord, last_uncertainty)
+    NIS = net.GetNIS(measure_coord, measure_uncertainty, temp_coord, temp_uncertainty)
+    labs = np.stack([load_label(label_paths[f], spec.image_size)[::8, ::8] for f in group])      # train.py:259-261
+    gt8, mask8 = labs[..., :3], labs[..., 3:4]
+    T = np.asarray(transform, np.float32)
+    scal = []
+    for c, u in ((measure_coord, measure_uncertainty), (temp_coord, temp_uncertainty), (KF_coord, KF_uncertainty)):
+        # the reference broadcasts the single estimated frame against both ground-truth frames of the batch (KFNet.py:214)
+        l, a = coord_loss_with_uncertainty(c.cpu().numpy(), u.cpu().numpy(), gt8, mask8, T)
+        scal += [l, a]
+    dev = measure_coord.device
+    return (measure_coord, measure_uncertainty, temp_coord, temp_uncertainty, KF_coord, KF_uncertainty, NIS, list(group),
+            scal[0], scal[1], scal[2], scal[3], scal[4], scal[5], torch.from_numpy(gt8).to(dev), torch.from_numpy(mask8).to(dev))
+
+
 def eval(image_list, label_list, transform_file, snapshot, scene="stairs", output_folder="", NIS=False,  # noqa: A001
          mode="fp32", chunk=16, weights=None, engine=None, quiet=False, device=None):
     import torch

@@ -78,13 +78,15 @@ class KFNet:
         assert t.shape[0] == B
         return t[..., :3], t[..., 3:4], k[..., :3], k[..., 3:4]
 
-    # ---------------------------------------------------------------- pointwise API-surface helpers
+    # ---------------------------------------------------------------- pointwise API surface (kfn_kalman_update)
     def BuildKFCoord(self, last_coord, last_uncertainty, measure_coord, measure_uncertainty):   # KFNet.py:148-162
-        lv, mv = last_uncertainty.square(), measure_uncertainty.square()
-        K = lv / (lv + mv)
-        omk = (1.0 - K).clamp_min(0.0)
-        return omk * last_coord + K * measure_coord, (omk * lv).sqrt()
+        prior = torch.cat([last_coord, last_uncertainty], -1).float().contiguous()
+        meas = torch.cat([measure_coord, measure_uncertainty], -1).float().contiguous()
+        post, _ = self.engine.kalman_update(prior, meas)
+        return post[..., :3], post[..., 3:4]
 
     def GetNIS(self, measure_coord_map, measure_uncertainty_map, temp_coord_map, temp_uncertainty_map):   # KFNet.py:174-184
-        iu = (temp_uncertainty_map.square() + measure_uncertainty_map.square()).sqrt()
-        return (measure_coord_map - temp_coord_map).square() / iu.square()
+        prior = torch.cat([temp_coord_map, temp_uncertainty_map], -1).float().contiguous()
+        meas = torch.cat([measure_coord_map, measure_uncertainty_map], -1).float().contiguous()
+        _, nis = self.engine.kalman_update(prior, meas, want_nis=True)
+        return nis

@@ -51,3 +51,27 @@ def test_eval_cli_matches_oracle_on_files(tmp_path, weights, capsys):
         assert err < 1e-4, (t, err)
         np.testing.assert_allclose(np.log(got[..., 3]), np.log(want[..., 3]), atol=1e-4)
     assert len(dists[0]) == T and all(np.isfinite(dists[2]))
+
+
+def test_kf_fusion_16_tuple(tmp_path, weights):
+    """Eager KF_fusion (train.py:241-266): same 16 outputs, same shapes, consistent with the recursive API."""
+    import cv2
+    from kfnet_b200 import KFNetDataSpec, eval as ev, synth
+    imgs, labels = synth.make_sequence(3, seed=6), synth.make_labels(3, seed=7)
+    ip, lp = [], []
+    for t in range(3):
+        a, b = tmp_path / f"{t}.png", tmp_path / f"{t}.bin"
+        cv2.imwrite(str(a), np.ascontiguousarray(imgs[t][..., ::-1])); labels[t].astype("<f4").tofile(b)
+        ip.append(str(a)); lp.append(str(b))
+    (tmp_path / "i.txt").write_text("\n".join(ip)); (tmp_path / "l.txt").write_text("\n".join(lp))
+    spec = KFNetDataSpec(scene="stairs")
+    lc = torch.zeros(1, 60, 80, 3).cuda(); lu = torch.ones(1, 60, 80, 1).cuda()
+    out = ev.KF_fusion(str(tmp_path / "i.txt"), str(tmp_path / "l.txt"), np.eye(4, dtype=np.float32), lc, lu, spec, index=1,
+                       weights=weights)
+    assert len(out) == 16 and out[7] == [0, 1]
+    for k, c in zip(range(7), (3, 1, 3, 1, 3, 1, 3)):
+        assert tuple(out[k].shape) == (1, 60, 80, c)
+    assert tuple(out[14].shape) == (2, 60, 80, 3) and tuple(out[15].shape) == (2, 60, 80, 1)
+    assert all(isinstance(v, float) for v in out[8:14])
+    c64, u64 = O.scoordnet(imgs[1:2].astype(np.float32), weights, torch.float64)
+    assert float((out[0].cpu().double() - c64).abs().max()) < 1e-3

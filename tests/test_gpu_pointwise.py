@@ -121,3 +121,15 @@ def test_softmax_flow_and_sigma_via_oflownet(eng, weights):
     assert decided.float().mean() > 0.95
     assert torch.equal(amax.cpu().reshape(-1)[decided], ex64["argmax"][decided]), "argmax must be bit-exact off near-ties"
     print("oracle fp32-vs-fp64 logits err", e_fp32_oracle)
+
+
+def test_kalman_update_and_nis_pointwise(eng):
+    """kfn_kalman_update (KFNet.BuildKFCoord / GetNIS without the warp) vs the oracle."""
+    g = torch.Generator().manual_seed(3)
+    prior = torch.randn(2, 8, 12, 4, generator=g); prior[..., 3] = torch.rand(2, 8, 12, generator=g) * 0.2 + 0.01
+    meas = torch.randn(2, 8, 12, 4, generator=g); meas[..., 3] = torch.rand(2, 8, 12, generator=g) * 0.2 + 0.01
+    post, nis = eng.kalman_update(prior.cuda().contiguous(), meas.cuda().contiguous(), want_nis=True)
+    kc, ku = O.build_kf_coord(prior[..., :3], prior[..., 3:4], meas[..., :3], meas[..., 3:4])
+    assert_close_rms(post.cpu(), torch.cat([kc, ku], -1), 2e-6, "posterior")
+    assert_close_rms(nis.cpu(), O.get_nis(meas[..., :3], meas[..., 3:4], prior[..., :3], prior[..., 3:4]), 2e-6, "nis")
+    assert bool((post[..., 3].cpu() <= prior[..., 3] + 1e-7).all())                 # sigma+ <= sigma-
