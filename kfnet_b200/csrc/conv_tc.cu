@@ -869,7 +869,10 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
 }
 
 int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};
+  int dev_ = 0;
+  KFN_CUDA_OK(cudaGetDevice(&dev_));
+  bool& attr_set = attr_set_dev[dev_ & 63];
   if (!attr_set) {
     const int max_smem = 201 * 1024 + 1024 + (int)kEpiStageBytes;
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));

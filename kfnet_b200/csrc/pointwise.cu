@@ -339,7 +339,10 @@ int launch_kalman_scan(const float* measure, const float* flow, const float* sig
   KFN_REQUIRE(smem <= 200 * 1024, "label grid too large for the shared-memory resident filter state");
   Xform X;
   for (int i = 0; i < 16; ++i) X.m[i] = T16_host[i];
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};
+  int dev_ = 0;
+  KFN_CUDA_OK(cudaGetDevice(&dev_));
+  bool& attr_set = attr_set_dev[dev_ & 63];
   if (!attr_set) {
     KFN_CUDA_OK(cudaFuncSetAttribute(kalman_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
