@@ -281,7 +281,7 @@ __device__ __forceinline__ void mma_role_x3(const TcParams& p, uint32_t smem_bas
     for (int tap = 0; tap < p.ntaps; ++tap) {
       for (int t = 0; t < p.n_terms; ++t) {
         const int acc = (p.la[t] == 0 && p.lw[t] == 0) ? (tap % 3) : 3;
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 128u;
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * p.acc_stride;
         for (int kc = 0; kc < p.cpk; ++kc) {
           mbar_wait(smem_u32(&s_full[s]), ph);
           tc_fence_after();
@@ -496,7 +496,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           if (p.x3acc) {
             for (int acc = 1; acc < 4; ++acc) {
               if (acc < 3 && acc >= n_main) continue;
-              tmem_ld32(taddr + (uint32_t)acc * 128u, r);
+              tmem_ld32(taddr + (uint32_t)acc * p.acc_stride, r);
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
             }
@@ -538,7 +538,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
             if (p.x3acc) {   // main splits 1, 2 and the correction accumulator, added with RN fp32
               for (int acc = 1; acc < 4; ++acc) {
                 if (acc < 3 && acc >= n_main) continue;
-                tmem_ld32(taddr + (uint32_t)acc * 128u + nc, r);
+                tmem_ld32(taddr + (uint32_t)acc * p.acc_stride + nc, r);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
               }
@@ -583,7 +583,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
             for (int acc = 1; acc < 4; ++acc) {
               if (acc < 3 && acc >= n_main) continue;
               float w[16];
-              tmem_ld16(taddr + (uint32_t)acc * 128u + nc, w);
+              tmem_ld16(taddr + (uint32_t)acc * p.acc_stride + nc, w);
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] += w[i];
             }
@@ -787,9 +787,15 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   // pipeline its full depth (or the layer is small anyway); big layers keep the whole SM
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * (uint32_t)BN) tmem_cols <<= 1;
-  if (x3) tmem_cols = 512;
+  if (x3) {   // four accumulators (3 main-term splits + corrections) of pow2(BN) columns each, single-buffered
+    uint32_t per = 32;
+    while (per < (uint32_t)BN) per <<= 1;
+    tmem_cols = 4 * per;
+    p.acc_stride = per;
+  } else {
+    p.acc_stride = tmem_cols / 2;
+  }
   p.tmem_cols = tmem_cols;
-  p.acc_stride = x3 ? 128u : tmem_cols / 2;
   const uint32_t stage_guess = ((uint32_t)(kBlockM + BN) * row_bytes + 1023u) & ~1023u;
   const bool streaming = g.ntaps == 1 && g.Cin / KC == 1 && (int64_t)g.N * g.MH * g.MW > (1 << 20);   // K=KC 1-tap GEMMs over big maps
   const bool two_ctas = tc_two_ctas_enabled() && !streaming && tmem_cols <= 256 && (12u * stage_guess <= 88u * 1024u || BN <= 64);
