@@ -1,0 +1,76 @@
+"""Size-independent properties of the path at the full 480x640 geometry (BASELINE configs[3] shape, shorter T):
+they hold for any weights / inputs, so they check the CUDA path where the CPU oracle is too slow to follow."""
+import numpy as np
+import pytest
+import torch
+
+from tests.golden import cases
+from tests.util import gpu_setup
+
+pytestmark = pytest.mark.gpu
+T = 12
+
+
+@pytest.fixture(scope="module")
+def staged(weights):
+    gpu_setup()
+    from kfnet_b200 import synth
+    from kfnet_b200.engine import Engine
+    eng = Engine(weights, mode="bf16", image_size=(480, 640))
+    imgs = torch.from_numpy(synth.make_sequence(T, seed=8, noise_frames=True)).cuda()
+    meas = eng.scoordnet(imgs)
+    feat = eng.oflow_feat(imgs)
+    flow, sigw, _, _ = eng.oflownet(feat[:-1].contiguous(), feat[1:].contiguous())
+    z = torch.zeros(1, 60, 80, 2, device="cuda")
+    flow_t = torch.cat([z, flow]).unsqueeze(0).contiguous()             # entry t belongs to the pair (t-1, t)
+    sigw_t = torch.cat([z[..., 0], sigw]).unsqueeze(0).contiguous()
+    return eng, imgs, meas.unsqueeze(0).contiguous(), feat, flow_t, sigw_t
+
+
+def test_flow_stays_inside_the_search_window(staged):
+    _, _, _, feat, flow_t, sigw_t = staged
+    assert float(flow_t.min()) >= -4.0 - 1e-5 and float(flow_t.max()) <= 3.0 + 1e-5     # soft-argmax over offsets in [-4,3]^2
+    assert bool((sigw_t[:, 1:] > 0).all())
+    np.testing.assert_allclose(feat.pow(2).sum(-1).cpu().numpy(), 1.0, atol=2e-3)       # l2-normalised features
+
+
+def test_posterior_never_exceeds_prior_and_gain_in_unit_interval(staged):
+    eng, _, meas, _, flow_t, sigw_t = staged
+    Tm = np.eye(4, dtype=np.float32)
+    r = eng.kalman_scan(meas, flow_t, sigw_t, Tm, reinit_period=500, diagnostics=True)
+    temp, kf = r["temp"][0, 1:], r["kf"][0, 1:]
+    assert bool((kf[..., 3] <= temp[..., 3] * (1 + 1e-6)).all())                        # sigma+ <= sigma-
+    assert bool((kf[..., 3] <= meas[0, 1:, ..., 3] * (1 + 1e-6)).all())                 # ... and <= sigma_z
+    assert bool((r["nis"][0, 1:] >= 0).all())
+    # frame 0 (re-init): outputs are the measurement, NIS is zero
+    assert torch.equal(r["kf"][0, 0], meas[0, 0]) and float(r["nis"][0, 0].abs().max()) == 0.0
+    # identity transform: saved map = (kf xyz, 1/sigma+)
+    assert torch.equal(r["out_map"][0, ..., :3], r["kf"][0, ..., :3])
+    np.testing.assert_allclose(r["out_map"][0, ..., 3].cpu().numpy(), (1.0 / r["kf"][0, ..., 3]).cpu().numpy(), rtol=1e-6)
+
+
+def test_chunked_scan_with_carried_state_is_bit_identical(staged):
+    eng, _, meas, _, flow_t, sigw_t = staged
+    Tm = cases.transform().astype(np.float32)
+    whole = eng.kalman_scan(meas, flow_t, sigw_t, Tm, reinit_period=5, diagnostics=True, want_state=True)
+    state, outs = None, []
+    for a, b in ((0, 3), (3, 4), (4, 9), (9, T)):
+        part = eng.kalman_scan(meas[:, a:b].contiguous(), flow_t[:, a:b].contiguous(), sigw_t[:, a:b].contiguous(), Tm,
+                               state_in=state, first_index=a, reinit_period=5, want_state=True)
+        state = part["state"]
+        outs.append(part["out_map"])
+    assert torch.equal(torch.cat(outs, 1), whole["out_map"]) and torch.equal(state, whole["state"])
+
+
+def test_graph_replay_and_batching_are_bit_identical(staged):
+    eng, imgs, _, _, _, _ = staged
+    Tm = cases.transform().astype(np.float32)
+    seq = imgs.unsqueeze(0).contiguous()
+    a = eng.eval_sequences(seq, Tm, reinit_period=500, frames_per_batch=5, pairs_per_batch=4).clone()
+    out = torch.empty_like(a)
+    eng.eval_sequences_graphed(seq, Tm, out, reinit_period=500, frames_per_batch=12, pairs_per_batch=11)
+    eng.eval_sequences_graphed(seq, Tm, out, reinit_period=500, frames_per_batch=12, pairs_per_batch=11)   # replay
+    assert torch.equal(a, out)
+    two = torch.cat([seq, seq]).contiguous()                                              # S = 2 identical sequences
+    b = eng.eval_sequences(two, Tm, reinit_period=500, frames_per_batch=7, pairs_per_batch=3)
+    assert torch.equal(b[0], a[0]) and torch.equal(b[1], a[0])
