@@ -64,6 +64,9 @@ struct ConvGeom {
   // merged conv2d_transpose: output columns [ph*phase_cout, (ph+1)*phase_cout) belong to sub-pixel phase ph = 2*py+px and
   // are written to pixel (my*2 + py, mx*2 + px), channels [out_coff, out_coff + phase_cout).  0 = plain layer.
   int phase_cout;
+  // dual output (tensor-core path): columns >= split_col go to a second NHWC tensor `out2` (channel stride out2_cs,
+  // channels from 0) at the same pixel -- lets two layers that read the same input share one GEMM (conv1a + feat1).
+  int split_col, out2_cs;
 };
 enum { EPI_NONE = 0, EPI_EXP_CH3 = 1, EPI_L2NORM = 2 };
 

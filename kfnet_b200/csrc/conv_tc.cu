@@ -63,6 +63,8 @@ struct __align__(8) TcParams {
   int n_terms, cpk, in_ls, w_cin, out_limbs, out_ls;
   uint32_t tmem_cols, acc_stride;   // TMEM columns allocated by this CTA (power of 2 >= 32) and columns per accumulator stage
   int phase_cout;               // merged conv2d_transpose phases (see ConvGeom)
+  int split_col, out2_cs;       // dual output: columns >= split_col -> out2 (bf16, generic 16-column path)
+  void* out2;
   int x3acc;                    // 1: four 128-column TMEM accumulators (3 main-term splits + corrections), single-buffered
   int la[6], lw[6];
   uint32_t epi_stage_off;       // byte offset (from the 1024-aligned smem base) of the epilogue staging area
@@ -461,6 +463,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
     };
     int my_ni;
     const int64_t my_off = row_off(row, my_ni);
+    const int64_t my_off2 = p.split_col ? my_off / ((int64_t)p.out_cs * esize) * p.out2_cs * 2 : 0;   // same pixel, other tensor
     int64_t wr_off[4];      // rows this lane writes in the coalesced pass: quad*32 + i*8 + lane/4
     int wr_ni[4];
 #pragma unroll
@@ -476,6 +479,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
       uint8_t* const tile_ptr = reinterpret_cast<uint8_t*>(p.out) + tile_off;
       const bool valid = n0 + my_ni < p.N;
       uint8_t* const orow = tile_ptr + my_off;
+      uint8_t* orow2 = nullptr;
+      if (p.split_col) {
+        const int64_t tile_pix = ((int64_t)n0 * p.OH + (it.th << p.lbh) * p.omul + p.oaddy) * p.OW + (it.tw << p.lbw) * p.omul + p.oaddx;
+        orow2 = reinterpret_cast<uint8_t*>(p.out2) + tile_pix * p.out2_cs * 2 + my_off2;
+      }
       const int a = p.x3acc ? 0 : (j & 1);
       const uint32_t aph = p.x3acc ? ((uint32_t)j & 1u) : ((uint32_t)(j >> 1) & 1u);
       mbar_wait(smem_u32(&s_tfull[a]), aph);
@@ -518,7 +526,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           bool wvalid[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) { wrow[i] = tile_ptr + wr_off[i]; wvalid[i] = n0 + wr_ni[i] < p.N; }
-          for (; nc + 32 <= p.BN && col0 + nc + 32 <= p.Cout && (p.phase_cout == 0 || (p.phase_cout & 31) == 0); nc += 32) {
+          const int fast_end = p.split_col ? p.split_col : p.Cout;
+          for (; nc + 32 <= p.BN && col0 + nc + 32 <= fast_end && (p.phase_cout == 0 || (p.phase_cout & 31) == 0); nc += 32) {
             if (((nc >> 5) & 1) != hsel) continue;
             uint32_t r[32];
             tmem_ld32(taddr + nc, r);
@@ -610,8 +619,10 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
             ph_off = ((int64_t)(ph >> 1) * p.OW + (ph & 1)) * p.out_cs * esize;
           }
           if (p.out_bf16) {
+            uint8_t* rowbase = orow;
+            if (p.split_col && c >= p.split_col) { rowbase = orow2; cc = c - p.split_col; }
             for (int l = 0; l < p.out_limbs; ++l) {
-              uint8_t* dst = orow + ph_off + ((int64_t)cc + (int64_t)l * p.out_ls) * 2;
+              uint8_t* dst = rowbase + ph_off + ((int64_t)cc + (int64_t)l * p.out_ls) * 2;
               if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                 uint4 o0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                 uint4 o1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
@@ -709,7 +720,7 @@ int tc_pick_kc(int Cin) { return (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 1
 int tc_cout_padded(int Cout) { return (Cout + 15) / 16 * 16; }
 
 int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int CoutP, const float* bias_padded,
-                    void* out, int out_bf16, int num_sms, TcConvPlan* plan) {
+                    void* out, int out_bf16, int num_sms, TcConvPlan* plan, void* out2) {
   PFN_encodeTiled encode = get_encode();
   if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found (no CUDA driver?)"); return KFN_ERR_CUDA; }
   KFN_REQUIRE(g.Cin % 16 == 0, "tensor-core conv needs Cin % 16 == 0");
@@ -771,6 +782,9 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   if (p.n_terms > 1) halo = false;
   p.x3acc = x3 ? 1 : 0;
   p.phase_cout = g.phase_cout;
+  p.split_col = out2 ? g.split_col : 0; p.out2_cs = g.out2_cs; p.out2 = out2;
+  if (out2) KFN_REQUIRE(g.split_col % 32 == 0 && g.split_col > 0 && g.split_col < g.Cout && out_bf16 && g.limbs_out <= 1 && g.phase_cout == 0,
+                        "dual-output layer shape");
   p.n_tiles = CoutP / BN;
   const uint32_t sbo16 = (uint32_t)(8 * row_bytes) >> 4;
   p.desc_hi = sbo16 | (1u << 14) | (layout_type << 29);   // bits 32-45 SBO, 46 version=1, 61-63 layout

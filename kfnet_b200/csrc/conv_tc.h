@@ -21,7 +21,7 @@ int tc_cout_padded(int Cout);     // weights are packed [tap][CoutP][Cin] bf16 w
 
 // in: bf16 NHWC activations; w_packed: bf16 [ntaps][CoutP][Cin]; bias_padded: fp32 [CoutP]; out: bf16 or fp32.
 int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int CoutP, const float* bias_padded,
-                    void* out, int out_bf16, int num_sms, TcConvPlan* plan);
+                    void* out, int out_bf16, int num_sms, TcConvPlan* plan, void* out2 = nullptr);
 int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st);
 
 }  // namespace kfn

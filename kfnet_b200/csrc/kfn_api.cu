@@ -1,6 +1,7 @@
 // C ABI of libkfnet_b200.so: handle, weights, workspace arena and the layer schedules of SCoordNet,
 // the OFlowNet feature tower, the OFlowNet U-Net + FC head, and the batched sequence evaluation.
 // See include/kfnet_b200.h for the contract and the reference functions each entry point replaces.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -206,10 +207,36 @@ int pack_op(kfn_handle* h, const std::string& key, const LayerSpec& L, int phase
   return KFN_OK;
 }
 
+// conv1a (ScoreNet, 3->64) and feat1 (Temporal, 3->16) as one K=32 GEMM over the shared im2col rows (BF16 mode).
+int pack_first_both(kfn_handle* h) {
+  const float* w1 = h->host_w["ScoreNet/conv1a/kernel"].data();
+  const float* b1 = h->host_w["ScoreNet/conv1a/bias"].data();
+  const float* w2 = h->host_w["Temporal/feat1/kernel"].data();
+  const float* b2 = h->host_w["Temporal/feat1/bias"].data();
+  PackedOp op;
+  op.Cin = 32; op.Cout = 80; op.CoutP = 80; op.ntaps = 1; op.relu = 1; op.stride = 1;
+  std::vector<__nv_bfloat16> pk((size_t)80 * 32, __float2bfloat16(0.f));
+  std::vector<float> bias(80, 0.f);
+  for (int co = 0; co < 80; ++co) {
+    const float* w = co < 64 ? w1 : w2;
+    const int cw = co < 64 ? 64 : 16, c = co < 64 ? co : co - 64;
+    bias[co] = co < 64 ? b1[co] : b2[co - 64];
+    for (int k = 0; k < 27; ++k) pk[(size_t)co * 32 + k] = __float2bfloat16(w[k * cw + c] * 0.00625f);
+  }
+  KFN_CUDA_OK(cudaMalloc(&op.w, pk.size() * sizeof(__nv_bfloat16)));
+  h->allocs.push_back(op.w);
+  KFN_CUDA_OK(cudaMemcpy(op.w, pk.data(), pk.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  KFN_CUDA_OK(cudaMalloc(&op.bias, 80 * sizeof(float)));
+  h->allocs.push_back(op.bias);
+  KFN_CUDA_OK(cudaMemcpy(op.bias, bias.data(), 80 * sizeof(float), cudaMemcpyHostToDevice));
+  h->ops["first#both"] = op;
+  return KFN_OK;
+}
+
 // Runs packed op `key`: in (NHWC, `in.C` channel stride, op.Cin channels read from channel 0 of `in.p`)
 // -> out channels [out_coff, out_coff + Cout) of `out` at pixel (my*omul + oaddy, mx*omul + oaddx).
 int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff, int MH, int MW, int omul, int oaddy,
-           int oaddx, int epi, bool out_fp32, cudaStream_t st) {
+           int oaddx, int epi, bool out_fp32, cudaStream_t st, void* out2 = nullptr, int split_col = 0, int out2_cs = 0) {
   auto it = h->ops.find(key);
   if (it == h->ops.end()) { set_error("unknown op " + key); return KFN_ERR_STATE; }
   const PackedOp& op = it->second;
@@ -227,6 +254,7 @@ int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
   g.OH = out.H; g.OW = out.W; g.out_cs = out.C * lo; g.out_coff = out_coff; g.Cout = op.Cout;
   g.omul = omul; g.oaddy = oaddy; g.oaddx = oaddx; g.relu = op.relu; g.epi = epi;
   g.phase_cout = op.phase_cout;
+  g.split_col = split_col; g.out2_cs = out2_cs;
   if (h->mode == KFN_MODE_FP32) {
     return launch_conv_simt(g, reinterpret_cast<const float*>(in.p), reinterpret_cast<const float*>(op.w), op.CoutP,
                             op.bias, reinterpret_cast<float*>(out.p), st);
@@ -235,7 +263,7 @@ int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
   auto pit = h->plans.find(pk);
   if (pit == h->plans.end()) {
     TcConvPlan plan;
-    int rc = prepare_conv_tc(g, in.p, op.w, op.CoutP, op.bias, out.p, out_fp32 ? 0 : 1, h->num_sms, &plan);
+    int rc = prepare_conv_tc(g, in.p, op.w, op.CoutP, op.bias, out.p, out_fp32 ? 0 : 1, h->num_sms, &plan, out2);
     if (rc != KFN_OK) { set_error(key + ": " + g_error); return rc; }
     if (h->plans.size() > 4096) h->plans.clear();
     pit = h->plans.emplace(pk, plan).first;
@@ -258,8 +286,9 @@ void* offs(void* p, int64_t elems, int es) { return p ? reinterpret_cast<uint8_t
 
 // ---------------------------------------------------------------------------------------------
 // `shared_pre`: optional already-preprocessed input (im2col / fp32) shared with the feature tower by kfn_eval_sequences
+// `feat1_out`: when given (BF16 mode, kfn_eval_sequences) conv1a also produces the tower's feat1 into this buffer
 int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, Arena& ar, cudaStream_t st, bool dry,
-                   void* shared_pre = nullptr) {
+                   void* shared_pre = nullptr, void* feat1_out = nullptr) {
   const int H = h->H, W = h->W, es = esize(h);
   const int64_t px = (int64_t)B * H * W;
   void* pre = shared_pre ? shared_pre : ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
@@ -273,7 +302,11 @@ int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, 
     if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 3), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
   } else {
     if (!shared_pre && (rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
-    if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
+    if (feat1_out && h->mode == KFN_MODE_BF16) {
+      if ((rc = run_op(h, "first#both", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 64), 0, H, W, 1, 0, 0, EPI_NONE, false, st,
+                       feat1_out, 64, 16)))
+        return rc;
+    } else if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
   }
   struct Step { const char* name; int div; int c; };
   const Step steps[] = {{"conv1b", 1, 64},  {"conv2a", 2, 256}, {"conv2b", 2, 256}, {"conv3a", 4, 512}, {"conv3b", 4, 512},
@@ -289,12 +322,13 @@ int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, 
   return conv(h, "ScoreNet/prediction", cur, act(measure, B, H / 8, W / 8, 4), 0, EPI_EXP_CH3, true, st);
 }
 
+// `feat1_done`: feat1's output buffer already filled by the fused first layer (see scoordnet_impl)
 int tower_impl(kfn_handle* h, const uint8_t* images, int B, float* feat, Arena& ar, cudaStream_t st, bool dry,
-               void* shared_pre = nullptr) {
+               void* shared_pre = nullptr, void* feat1_done = nullptr) {
   const int H = h->H, W = h->W, es = esize(h);
   const int64_t px = (int64_t)B * H * W;
   void* pre = shared_pre ? shared_pre : ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
-  void* bufA = ar.alloc(px * 16 * es);
+  void* bufA = feat1_done ? feat1_done : ar.alloc(px * 16 * es);
   void* bufB = ar.alloc(px * 16 * es);
   if (dry) return KFN_OK;
   if (ar.overflow) { set_error("workspace too small for oflow_feat_forward"); return KFN_ERR_WORKSPACE; }
@@ -304,7 +338,7 @@ int tower_impl(kfn_handle* h, const uint8_t* images, int B, float* feat, Arena& 
     if ((rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 3), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
   } else {
     if (!shared_pre && (rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
-    if ((rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
+    if (!feat1_done && (rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
   }
   struct Step { const char* name; int div; int c; };
   const Step steps[] = {{"feat2", 2, 32}, {"feat3", 2, 32}, {"feat4", 4, 64}, {"feat5", 4, 64}, {"feat6", 8, 128}};
@@ -472,6 +506,10 @@ int kfn_finalize_weights(kfn_handle* h) {
       if ((rc = pack_op(h, key, L, 0, false, oh, oh, ih, ih))) return rc;
     }
   }
+  if (h->mode == KFN_MODE_BF16) {
+    // "first#both": conv1a (64) and feat1 (16) read the same im2col rows -> one GEMM with N = 80, dual output
+    if ((rc = pack_first_both(h))) return rc;
+  }
   h->finalized = true;
   return KFN_OK;
 }
@@ -487,6 +525,7 @@ int64_t kfn_workspace_bytes(kfn_handle* h, int frames, int pairs) {
     Arena c(nullptr, 0); oflownet_impl(h, nullptr, nullptr, pairs, nullptr, nullptr, nullptr, nullptr, c, nullptr, true);
     need = c.off > need ? c.off : need;
   }
+  if (frames > 0) need += (int64_t)frames * h->H * h->W * 16 * 2 + 1024;   // fused first layer's feat1 buffer (kfn_eval_sequences)
   return need + 4096;
 }
 
@@ -579,10 +618,13 @@ int kfn_eval_sequences(kfn_handle* h, const uint8_t* images, int S, int T, const
     if (a.overflow) { set_error("workspace too small for eval_sequences"); return KFN_ERR_WORKSPACE; }
     if (h->mode == KFN_MODE_FP32) { if ((rc = launch_preprocess_f32(images + f0 * img_bytes, (float*)pre, px * 3, st))) return rc; }
     else { if ((rc = launch_im2col27_bf16(images + f0 * img_bytes, (__nv_bfloat16*)pre, B, h->H, h->W, st))) return rc; }
+    static const bool fuse_first = [] { const char* e = getenv("KFN_FUSE_FIRST"); return !(e && e[0] == '0'); }();   // A/B switch
+    void* f1 = (h->mode == KFN_MODE_BF16 && fuse_first) ? a.alloc(px * 16 * 2) : nullptr;   // feat1 output, produced by the fused first layer
+    if (a.overflow) { set_error("workspace too small for eval_sequences"); return KFN_ERR_WORKSPACE; }
     const int64_t mark = a.off;
-    if ((rc = scoordnet_impl(h, images + f0 * img_bytes, B, measure + f0 * P * 4, a, st, false, pre))) return rc;
+    if ((rc = scoordnet_impl(h, images + f0 * img_bytes, B, measure + f0 * P * 4, a, st, false, pre, f1))) return rc;
     a.off = mark;
-    if ((rc = tower_impl(h, images + f0 * img_bytes, B, feat + f0 * P * 32, a, st, false, pre))) return rc;
+    if ((rc = tower_impl(h, images + f0 * img_bytes, B, feat + f0 * P * 32, a, st, false, pre, f1))) return rc;
   }
   // 2. process system: pair (f-1, f) for every flat frame f >= 1.  Pairs that straddle two sequences are computed and
   //    ignored (frame 0 of every sequence re-initialises the filter, eval.py:94-101).
