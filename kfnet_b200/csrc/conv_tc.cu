@@ -61,6 +61,7 @@ struct __align__(8) TcParams {
   int pf_dist;                  // L2 prefetch distance in tiles (0 = off)
   // bf16x3: k-chunks = n_terms x cpk; term t multiplies A limb la[t] with W limb lw[t]
   int n_terms, cpk, in_ls, w_cin, out_limbs, out_ls;
+  int epi_warps;                // 8 (320-thread CTA) or 4 (192-thread CTA, three CTAs per SM)
   uint32_t tmem_cols, acc_stride;   // TMEM columns allocated by this CTA (power of 2 >= 32) and columns per accumulator stage
   int phase_cout;               // merged conv2d_transpose phases (see ConvGeom)
   int split_col, out2_cs;       // dual output: columns >= split_col -> out2 (bf16, generic 16-column path)
@@ -323,7 +324,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&s_tfull[a]), 1);
-      mbar_init(smem_u32(&s_tempty[a]), kEpiWarps);
+      mbar_init(smem_u32(&s_tempty[a]), (uint32_t)p.epi_warps);
     }
     mbar_init(smem_u32(&s_wbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -528,7 +529,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           for (int i = 0; i < 4; ++i) { wrow[i] = tile_ptr + wr_off[i]; wvalid[i] = n0 + wr_ni[i] < p.N; }
           const int fast_end = p.split_col ? p.split_col : p.Cout;
           for (; nc + 32 <= p.BN && col0 + nc + 32 <= fast_end && (p.phase_cout == 0 || (p.phase_cout & 31) == 0); nc += 32) {
-            if (((nc >> 5) & 1) != hsel) continue;
+            if (p.epi_warps == 8 && ((nc >> 5) & 1) != hsel) continue;
             uint32_t r[32];
             tmem_ld32(taddr + nc, r);
             const int c = col0 + nc;
@@ -585,7 +586,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           }
         }
         for (; nc < p.BN; nc += 16) {
-          if (((nc >> 4) & 1) != hsel) continue;
+          if (p.epi_warps == 8 && ((nc >> 4) & 1) != hsel) continue;
           float v[16];
           tmem_ld16(taddr + nc, v);
           if (p.x3acc) {
@@ -708,6 +709,10 @@ bool tc_two_ctas_enabled() {
   static const bool on = [] { const char* e = getenv("KFN_TC_TWO_CTAS"); return !(e && e[0] == '0'); }();
   return on;
 }
+bool tc_three_ctas_enabled() {
+  static const bool on = [] { const char* e = getenv("KFN_TC_THREE_CTAS"); return !(e && e[0] == '0'); }();
+  return on;
+}
 bool tc_pdl_enabled() {
   static const bool on = [] { const char* e = getenv("KFN_TC_PDL"); return !(e && e[0] == '0'); }();
   return on;
@@ -813,8 +818,11 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   const uint32_t stage_guess = ((uint32_t)(kBlockM + BN) * row_bytes + 1023u) & ~1023u;
   const bool streaming = g.ntaps == 1 && g.Cin / KC == 1 && (int64_t)g.N * g.MH * g.MW > (1 << 20);   // K=KC 1-tap GEMMs over big maps
   const bool two_ctas = tc_two_ctas_enabled() && !streaming && tmem_cols <= 256 && (12u * stage_guess <= 88u * 1024u || BN <= 64);
-  plan->ctas_per_sm = two_ctas ? 2 : 1;
-  const uint32_t budget = two_ctas ? 88 * 1024 : 200 * 1024;   // 2 x (88 + 16 staging + 1 align + static) KB fits the 228 KB SM
+  // three CTAs/SM (192 threads, 4 epilogue warps, 56 KB pipeline) for the narrowest layers
+  const bool three_ctas = two_ctas && tc_three_ctas_enabled() && tmem_cols <= 128 && 6u * stage_guess <= 56u * 1024u;
+  plan->ctas_per_sm = three_ctas ? 3 : two_ctas ? 2 : 1;
+  p.epi_warps = three_ctas ? 4 : 8;
+  const uint32_t budget = three_ctas ? 56 * 1024 : two_ctas ? 88 * 1024 : 200 * 1024;   // n x (budget + staging + 1 KB + static) fits the 228 KB SM
   cuuint64_t dimA[5], strA[4];
   cuuint32_t boxA[5];
   if (halo) {
@@ -827,13 +835,13 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     for (int t = 0; t < g.ntaps; ++t)
       p.tap_off16[t] = (uint32_t)(((1 + g.dy[t]) * 10 * hbn + (1 + g.dx[t])) * row_bytes) >> 4;
     uint32_t hb = budget;
-    if (w_total + 3 * p.stage_bytes > hb) { hb = 200 * 1024; plan->ctas_per_sm = 1; }
+    if (w_total + 3 * p.stage_bytes > hb) { hb = 200 * 1024; plan->ctas_per_sm = 1; p.epi_warps = 8; }
     int stages = (int)((hb - w_total) / p.stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     KFN_REQUIRE(stages >= 2, "halo pipeline needs at least 2 stages");
     p.stages = stages;
     p.epi_stage_off = w_total + (uint32_t)stages * p.stage_bytes;
-    plan->smem = (size_t)p.epi_stage_off + kEpiStageBytes + 1024;
+    plan->smem = (size_t)p.epi_stage_off + (size_t)p.epi_warps * 2048 + 1024;
     // halo view: dims (c, w, n, h, 1) so that the box lands in smem as [y][n][x] rows
     dimA[0] = g.Cin; dimA[1] = g.IW; dimA[2] = g.N; dimA[3] = g.IH; dimA[4] = 1;
     strA[0] = cs; strA[1] = cs * g.IW * g.IH; strA[2] = cs * g.IW; strA[3] = cs * g.IW * g.IH * g.N;
@@ -851,7 +859,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     KFN_REQUIRE(stages >= 2, "pipeline needs at least 2 stages");
     p.stages = stages;
     p.epi_stage_off = (uint32_t)p.stages * p.stage_bytes;
-    plan->smem = (size_t)p.epi_stage_off + kEpiStageBytes + 1024;
+    plan->smem = (size_t)p.epi_stage_off + (size_t)p.epi_warps * 2048 + 1024;
     boxA[0] = (cuuint32_t)KC; boxA[1] = (cuuint32_t)bw; boxA[2] = 1u; boxA[3] = (cuuint32_t)bh; boxA[4] = (cuuint32_t)bn;
     if (g.istride == 1) {
       dimA[0] = (cuuint64_t)(limbs_a - 1) * p.in_ls + g.Cin; dimA[1] = g.IW; dimA[2] = 1; dimA[3] = g.IH; dimA[4] = g.N;
@@ -904,7 +912,7 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)plan.grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(plan.ctas_per_sm == 3 ? 192 : kThreads);
   cfg.dynamicSmemBytes = plan.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -912,7 +920,7 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
-  if (plan.ctas_per_sm == 2)
+  if (plan.ctas_per_sm >= 2)
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_x2, tmA[0], tmA[1], p));
   else
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel, tmA[0], tmA[1], p));

@@ -15,6 +15,7 @@ struct TcConvPlan {
 bool tc_halo_enabled();           // KFN_TC_HALO=0 disables the halo-tile variant (A/B measurements)
 bool tc_prefetch_enabled();       // KFN_TC_PREFETCH=1 enables the producer TMA L2 prefetch (measured: no gain, off by default)
 bool tc_two_ctas_enabled();       // KFN_TC_TWO_CTAS=0: always one CTA per SM (A/B measurements)
+bool tc_three_ctas_enabled();     // KFN_TC_THREE_CTAS=0: at most two CTAs per SM (A/B measurements)
 bool tc_pdl_enabled();            // KFN_TC_PDL=0: plain stream-ordered launches (A/B measurements)
 int tc_pick_kc(int Cin);          // channels per k-block: 64 / 32 / 16 (128B / 64B / 32B swizzle)
 int tc_cout_padded(int Cout);     // weights are packed [tap][CoutP][Cin] bf16 with CoutP = roundup(Cout, 16)
