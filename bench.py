@@ -259,6 +259,31 @@ def run_ours(args):
     t_dv = stage_ms(lambda: eng.diff_volume(fp_, fc_, bf16=(args.mode != "fp32"), out=dv_out), reps=10)
     pk = peaks()
     tf_ach = GFLOP_SCOORDNET * B / t_sc            # GFLOP / ms = TFLOP/s
+    # the dominant single launch: conv4b (3x3, 1024->1024 on the 60x80 grid), timed per launch through kfn_conv_layer
+    roof_launch = None
+    if args.mode == "bf16":
+        x4 = (torch.randn(B, eng.GH, eng.GW, 1024, device="cuda") * 0.2).to(torch.bfloat16)
+        y4 = torch.empty(B, eng.GH, eng.GW, 1024, device="cuda", dtype=torch.bfloat16)
+        t_c4 = stage_ms(lambda: eng.conv_layer("ScoreNet/conv4b", x4, (eng.GH, eng.GW), 1024, out=y4), reps=20)
+        gflop_c4 = 2.0 * B * eng.GH * eng.GW * 9 * 1024 * 1024 / 1e9
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same launch from the committed `ncu --set full` capture
+            import csv
+            import glob
+            f = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_prof_conv_tc_ncu_summary.csv")))[-1]
+            rows = list(csv.reader(open(f)))
+            d = dict(zip(rows[0], rows[2]))
+            traffic = {"bytes": (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])) * 1e6,
+                       "algorithmic_bytes": B * eng.GH * eng.GW * 1024 * 2 * 2 + 9 * 1024 * 1024 * 2,
+                       "tensor_pipe_active_pct": float(d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]),
+                       "source": os.path.basename(f) + " (conv4b at batch 16)"}
+        except Exception:
+            pass
+        roof_launch = {"bound": "tensor", "kernel": "conv_tc_kernel, ScoreNet/conv4b, one launch, batch %d" % B,
+                       "achieved": gflop_c4 / t_c4, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": gflop_c4 / t_c4 / pk["tf_burst"],
+                       "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "flops_per_launch": gflop_c4 * 1e9,
+                       "ms_per_launch": t_c4, "traffic": traffic}
+        del x4, y4
     dv_bytes = ppb * (2 * 60 * 80 * 32 * 4 + 4800 * 64 * 32 * (2 if args.mode == "bf16" else 4))
     frames_total = world * T * args.steps
     fps = frames_total / (ms / 1e3)
@@ -280,9 +305,10 @@ def run_ours(args):
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(T * H * W * 3),
                     "d2h_bytes_per_step": int(T * eng.GH * eng.GW * 16)},
             "gpu_launches": int(launches * args.steps),
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (SCoordNet stack, %d launches per batch of %d frames incl. 1 im2col)" % (n_sc, B),
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel over the SCoordNet stack (%d launches per batch of %d frames incl. 1 im2col; 63 %% of the step)" % (n_sc, B),
                          "achieved": tf_ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf_ach / pk["tf_sustained"],
                          "peak_source": pk["src"] + " bf16 sustained", "traffic": None},
+            "roofline_dominant_launch": roof_launch,
             "stages_ms": {"scoordnet_per_batch": t_sc, "tower_per_batch": t_tw, "oflownet_per_pair_batch": t_of,
                           "diff_volume_per_pair_batch": t_dv,
                           "diff_volume_GBps": dv_bytes / t_dv / 1e6, "diff_volume_frac_hbm": dv_bytes / t_dv / 1e6 / pk["hbm"]},
