@@ -1,6 +1,9 @@
 // Memory-bound kernels of the KFNet path: input preprocessing, feature-difference volume,
 // softmax -> soft-argmax flow, and the serial warp + Kalman scan.  Compiled with --fmad=false so the
 // few flops here round exactly like the reference's separate fp32 TF ops (mul, add, div, sqrt).
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace kfn {
@@ -330,11 +333,153 @@ kalman_scan_kernel(const float4* __restrict__ measure, const float2* __restrict_
   }
 }
 
+// Cluster variant: the single-CTA scan above is instruction-issue bound on its one SM (~180 instructions per pixel),
+// so a sequence is spread over a thread-block cluster of kScanCluster CTAs.  Each CTA owns a band of label-grid rows
+// and keeps that band's state (double-buffered) in its own shared memory; the bilinear taps of the warp read whichever
+// CTA owns the sampled row through distributed shared memory (cluster.map_shared_rank), and one cluster.sync() per
+// frame replaces the __syncthreads().  Same arithmetic, same order: results are bit-identical to the single-CTA kernel.
+namespace cg = cooperative_groups;
+constexpr int kScanCluster = 4;
+
+__global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(1024, 1)
+kalman_scan_cluster_kernel(const float4* __restrict__ measure, const float2* __restrict__ flow, const float* __restrict__ sigma_w,
+                           const float4* __restrict__ state_in, float4* __restrict__ state_out, Xform X, int T, int GH, int GW,
+                           int first_index, int reinit_period, int nis_gate, float4* __restrict__ out_map,
+                           float4* __restrict__ temp, float4* __restrict__ kf, float* __restrict__ nis, int2* __restrict__ taps) {
+  extern __shared__ float4 s_band[];           // [2][cap]  this CTA's rows of the state
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int s = blockIdx.x / kScanCluster;
+  const int P = GH * GW;
+  const int rows_per = (GH + kScanCluster - 1) / kScanCluster;
+  const int cap = rows_per * GW;
+  const int y_lo = rank * rows_per;
+  const int y_hi = min(GH, y_lo + rows_per);
+  const int nloc = max(0, y_hi - y_lo) * GW;   // pixels owned by this CTA
+  const int p_lo = y_lo * GW;
+  const float4* band[kScanCluster];            // every CTA's band, through distributed shared memory
+#pragma unroll
+  for (int r = 0; r < kScanCluster; ++r) band[r] = cluster.map_shared_rank(s_band, r);
+  const int64_t seq = (int64_t)s * T * P;
+  int cur = 0;
+  if (state_in) {
+    for (int i = threadIdx.x; i < nloc; i += blockDim.x) s_band[i] = state_in[(int64_t)s * P + p_lo + i];
+  }
+  cluster.sync();
+  const float xmax = (float)(GW - 1), ymax = (float)(GH - 1);
+  const float minvar = 1e-5f * 1e-5f;
+  const bool need_nis = (nis != nullptr) || (nis_gate != 0);
+  auto gather = [&](int iy, int ix) -> float4 {
+    const int r = iy / rows_per;
+    return band[r][cur * cap + (iy - r * rows_per) * GW + ix];
+  };
+  for (int t = 0; t < T; ++t) {
+    const int64_t fr = seq + (int64_t)t * P;
+    const int idx = first_index + t;
+    const bool reinit = (reinit_period > 0) && (idx % reinit_period == 0);
+    float4* nxt = s_band + (cur ^ 1) * cap;
+    for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
+      const int p = p_lo + i;
+      const float4 z = measure[fr + p];
+      float4 xm, xp;
+      float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+      int2 tp = make_int2(0, 0);
+      if (reinit) {
+        xm = z; xp = z;
+      } else {
+        const float2 fl = flow[fr + p];
+        const int y = p / GW, x = p - y * GW;
+        const float cx = (float)x + fl.x, cy = (float)y + fl.y;
+        const float x0 = floorf(cx), y0 = floorf(cy);
+        const float x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+        const float x0s = fminf(fmaxf(x0, 0.f), xmax), x1s = fminf(fmaxf(x1, 0.f), xmax);
+        const float y0s = fminf(fmaxf(y0, 0.f), ymax), y1s = fminf(fmaxf(y1, 0.f), ymax);
+        const float wx0 = x1s - cx, wx1 = cx - x0s, wy0 = y1s - cy, wy1 = cy - y0s;
+        const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
+        const int ix0 = (int)x0s, ix1 = (int)x1s, iy0 = (int)y0s, iy1 = (int)y1s;
+        const float4 i00 = gather(iy0, ix0), i01 = gather(iy1, ix0);
+        const float4 i10 = gather(iy0, ix1), i11 = gather(iy1, ix1);
+        xm.x = ((w00 * i00.x + w01 * i01.x) + w10 * i10.x) + w11 * i11.x;
+        xm.y = ((w00 * i00.y + w01 * i01.y) + w10 * i10.y) + w11 * i11.y;
+        xm.z = ((w00 * i00.z + w01 * i01.z) + w10 * i10.z) + w11 * i11.z;
+        const float sl = ((w00 * i00.w + w01 * i01.w) + w10 * i10.w) + w11 * i11.w;
+        const float sw = sigma_w[fr + p];
+        const float last_var = fmaxf(sl * sl, minvar);
+        const float trans_var = fmaxf(sw * sw, minvar);
+        xm.w = sqrtf(trans_var + last_var);
+        const float lv = xm.w * xm.w, mv = z.w * z.w;
+        const float K = lv / (lv + mv);
+        const float omk = fmaxf(1.0f - K, 0.0f);
+        xp.x = omk * xm.x + K * z.x;
+        xp.y = omk * xm.y + K * z.y;
+        xp.z = omk * xm.z + K * z.z;
+        xp.w = sqrtf(omk * lv);
+        if (need_nis) {
+          const float iu = sqrtf(lv + mv);
+          const float iv = iu * iu;
+          const float d0 = z.x - xm.x, d1 = z.y - xm.y, d2 = z.z - xm.z;
+          n0 = (d0 * d0) / iv; n1 = (d1 * d1) / iv; n2 = (d2 * d2) / iv;
+        }
+        tp = make_int2((int)x0, (int)y0);
+      }
+      nxt[i] = xp;
+      float4 src = xp;
+      if (nis_gate && !reinit && ((n0 + n1) + n2 > 7.815f)) { src.x = z.x; src.y = z.y; src.z = z.z; }
+      float4 o;
+      o.x = ((X.m[0] * src.x + X.m[1] * src.y) + X.m[2] * src.z) + X.m[3];
+      o.y = ((X.m[4] * src.x + X.m[5] * src.y) + X.m[6] * src.z) + X.m[7];
+      o.z = ((X.m[8] * src.x + X.m[9] * src.y) + X.m[10] * src.z) + X.m[11];
+      o.w = 1.0f / xp.w;
+      out_map[fr + p] = o;
+      if (temp) temp[fr + p] = xm;
+      if (kf) kf[fr + p] = xp;
+      if (nis) { nis[(fr + p) * 3 + 0] = n0; nis[(fr + p) * 3 + 1] = n1; nis[(fr + p) * 3 + 2] = n2; }
+      if (taps) taps[fr + p] = tp;
+    }
+    cluster.sync();                            // all bands of frame t written before anyone gathers for frame t+1
+    cur ^= 1;
+  }
+  if (state_out) {
+    for (int i = threadIdx.x; i < nloc; i += blockDim.x) state_out[(int64_t)s * P + p_lo + i] = s_band[cur * cap + i];
+  }
+  cluster.sync();                              // no CTA may exit while a peer can still read its shared memory
+}
+
 int launch_kalman_scan(const float* measure, const float* flow, const float* sigma_w, const float* state_in,
                        float* state_out, const float* T16_host, int S, int T, int GH, int GW, int first_index,
                        int reinit_period, int nis_gate, float* out_map, float* temp, float* kf, float* nis,
                        int32_t* taps, cudaStream_t st) {
   KFN_REQUIRE(S > 0 && T > 0 && GH > 0 && GW > 0, "empty scan");
+  static const bool use_cluster = [] { const char* e = getenv("KFN_SCAN_CLUSTER"); return !(e && e[0] == '0'); }();
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev0 = 0;
+    KFN_CUDA_OK(cudaGetDevice(&dev0));
+    KFN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev0));
+  }
+  // latency regime only: with many sequences one CTA per sequence already fills the SMs (measured: 148 sequences run
+  // 8.2 us/frame-step single-CTA vs 25 us as 592 cluster CTAs; 8 sequences run 7.2 vs 4.8 us/frame)
+  if (use_cluster && GH >= 2 * kScanCluster && 2 * S * kScanCluster <= num_sms) {
+    Xform Xc;
+    for (int i = 0; i < 16; ++i) Xc.m[i] = T16_host[i];
+    const int rows_per = (GH + kScanCluster - 1) / kScanCluster;
+    const size_t smem_c = (size_t)2 * rows_per * GW * sizeof(float4);
+    KFN_REQUIRE(smem_c <= 200 * 1024, "label grid too large for the cluster scan");
+    static bool attr_dev[64] = {false};
+    int dev_c = 0;
+    KFN_CUDA_OK(cudaGetDevice(&dev_c));
+    if (!attr_dev[dev_c & 63]) {
+      KFN_CUDA_OK(cudaFuncSetAttribute(kalman_scan_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_dev[dev_c & 63] = true;
+    }
+    kalman_scan_cluster_kernel<<<S * kScanCluster, 1024, smem_c, st>>>(
+        reinterpret_cast<const float4*>(measure), reinterpret_cast<const float2*>(flow), sigma_w,
+        reinterpret_cast<const float4*>(state_in), reinterpret_cast<float4*>(state_out), Xc, T, GH, GW, first_index,
+        reinit_period, nis_gate, reinterpret_cast<float4*>(out_map), reinterpret_cast<float4*>(temp),
+        reinterpret_cast<float4*>(kf), nis, reinterpret_cast<int2*>(taps));
+    KFN_LAUNCH_OK();
+    return KFN_OK;
+  }
   const size_t smem = (size_t)2 * GH * GW * sizeof(float4);
   KFN_REQUIRE(smem <= 200 * 1024, "label grid too large for the shared-memory resident filter state");
   Xform X;
