@@ -207,6 +207,13 @@ def run_ours(args):
         if world > 1:
             gather_outputs(out, world)
 
+    def step_e2e_cabi():
+        # ONE C-ABI call with HOST buffers (kfn_eval_sequences_host): H2D of the frames batch by batch on the library's
+        # copy stream, the whole path, D2H of the maps, stream synchronised before it returns
+        eng.eval_sequences_host(host_imgs, Tm, host_out, reinit_period=500, frames_per_batch=fpb, pairs_per_batch=ppb)
+        if world > 1:
+            gather_outputs(eng._host_stage[1], world)
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
@@ -236,7 +243,8 @@ def run_ours(args):
     launches = eng.launch_count()
     ms = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps, max(4, args.warmup))      # >= 4: both staging buffers get their graph captured in warm-up
+    ms_e2e_pipe = timed(step_e2e, args.steps, max(4, args.warmup))      # >= 4: both staging buffers get their graph captured in warm-up
+    ms_e2e = timed(step_e2e_cabi, args.steps, args.warmup)
 
     # per-stage device times on this rank (events on the launching stream), for the roofline of the dominant kernel
     def stage_ms(fn, reps=3):
@@ -303,7 +311,10 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (%.0f MB of uint8 images per step)" % (T * H * W * 3 / 1e6)},
             "clocks": clocks,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(T * H * W * 3),
-                    "d2h_bytes_per_step": int(T * eng.GH * eng.GW * 16)},
+                    "d2h_bytes_per_step": int(T * eng.GH * eng.GW * 16),
+                    "api": "kfn_eval_sequences_host (one C-ABI call per step, pinned host buffers in/out, synchronous)"},
+            "e2e_pipelined": {"value": frames_total / (ms_e2e_pipe / 1e3), "unit": "frames/s",
+                              "api": "Engine.eval_sequences_graphed + double-buffered H2D across steps (CUDA graph replay)"},
             "gpu_launches": int(launches * args.steps),
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel over the SCoordNet stack (%d launches per batch of %d frames incl. 1 im2col; 63 %% of the step)" % (n_sc, B),
                          "achieved": tf_ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf_ach / pk["tf_sustained"],

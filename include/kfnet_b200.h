@@ -11,7 +11,7 @@
  *  - All tensors are dense NHWC.  Device pointers are caller-owned (torch-allocated); the library
  *    owns only the opaque handle (packed weights, TMA descriptors, scratch it allocates at finalize).
  *  - Calls enqueue work on `stream` (a cudaStream_t passed as void*) and return; no host sync,
- *    except the *_host entry point which takes HOST buffers and synchronises before returning.
+ *    except kfn_eval_sequences_host, which takes HOST buffers and synchronises before returning.
  *  - One handle per device / rank; a handle is not thread-safe.
  *  - There is NO CPU fallback: without a CUDA device kfn_create fails with KFN_ERR_CUDA.
  */
@@ -64,7 +64,7 @@ enum kfn_mode { KFN_MODE_FP32 = 0, KFN_MODE_BF16 = 1, KFN_MODE_BF16X3 = 2 };
 KFN_API const char* kfn_version(void);
 KFN_API const char* kfn_last_error(void);
 
-/* image_h / image_w must be multiples of 64 (reference: 480x640, KFNetDataSpec.image_size KFNet.py:9). */
+/* image_h / image_w must be multiples of 8 (reference: 480x640, KFNetDataSpec.image_size KFNet.py:9). */
 KFN_API int kfn_create(kfn_handle** out, int device, int mode, int image_h, int image_w);
 KFN_API int kfn_destroy(kfn_handle* h);
 
@@ -150,6 +150,14 @@ KFN_API int64_t kfn_sequence_extra_bytes(kfn_handle* h, int S, int T);
 KFN_API int kfn_eval_sequences(kfn_handle* h, const uint8_t* images, int S, int T, const float* transform,
                        int reinit_period, int nis_gate, int frames_per_batch, int pairs_per_batch,
                        float* out_map, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The same with HOST buffers -- the end-to-end entry point: `host_images` uint8 [S,T,H,W,3] (pinned memory recommended) are
+ * streamed to the caller-owned device staging buffer `dev_images` batch by batch on an internal copy stream (each frame
+ * batch's kernels wait only for that batch), the path runs on `stream`, the maps are copied to `host_out`
+ * fp32 [S,T,GH,GW,4] through `dev_out`, and the call returns after synchronising `stream`. */
+KFN_API int kfn_eval_sequences_host(kfn_handle* h, const uint8_t* host_images, int S, int T, const float* transform,
+                            int reinit_period, int nis_gate, int frames_per_batch, int pairs_per_batch, float* host_out,
+                            uint8_t* dev_images, float* dev_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* One packed layer of the path by name (per-layer parity tests and per-layer roofline measurements).
  *   op_key: "<scope>/<layer>" for conv / dense layers, "<scope>/<layer>#p<k>" (k = 2*py+px) for one sub-pixel phase

@@ -28,6 +28,7 @@ SIGNATURES = {
     "kfn_kalman_update": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "kfn_sequence_extra_bytes": (_i64, [_vp, _i, _i]),
     "kfn_eval_sequences": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
+    "kfn_eval_sequences_host": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp]),
     "kfn_conv_layer": (_i, [_vp, C.c_char_p, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "kfn_launch_count": (_i64, [_vp, _i]),
 }

@@ -87,6 +87,10 @@ struct kfn_handle {
   std::vector<void*> allocs;
   std::map<std::tuple<std::string, const void*, void*, int>, TcConvPlan> plans;
   bool finalized = false;
+  // kfn_eval_sequences_host: internal copy stream and per-batch events (library-owned)
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
+  cudaEvent_t compute_done = nullptr;
 };
 
 namespace {
@@ -437,6 +441,9 @@ int kfn_destroy(kfn_handle* h) {
   if (!h) return KFN_OK;
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);
+  if (h->compute_done) cudaEventDestroy(h->compute_done);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
   return KFN_OK;
 }
@@ -589,13 +596,13 @@ int64_t kfn_sequence_extra_bytes(kfn_handle* h, int S, int T) {
   return F * P * (4 + 32 + 2 + 1) * 4 + 8 * 1024;
 }
 
-int kfn_eval_sequences(kfn_handle* h, const uint8_t* images, int S, int T, const float* transform, int reinit_period,
-                       int nis_gate, int frames_per_batch, int pairs_per_batch, float* out_map, void* workspace,
-                       int64_t workspace_bytes, void* stream) {
-  KFN_READY(h);
-  KFN_REQUIRE(images && transform && out_map && workspace, "null argument");
-  KFN_REQUIRE(S > 0 && T > 0 && frames_per_batch > 0 && pairs_per_batch > 0, "empty problem");
-  cudaStream_t st = (cudaStream_t)stream;
+}  // extern "C"
+
+namespace {
+// `batch_ready`: optional events, one per frame batch, the compute stream waits on before touching that batch's images
+int eval_sequences_impl(kfn_handle* h, const uint8_t* images, int S, int T, const float* transform, int reinit_period,
+                        int nis_gate, int frames_per_batch, int pairs_per_batch, float* out_map, void* workspace,
+                        int64_t workspace_bytes, cudaStream_t st, const cudaEvent_t* batch_ready) {
   const int64_t F = (int64_t)S * T, P = (int64_t)h->GH * h->GW;
   Arena top(workspace, workspace_bytes);
   float* measure = (float*)top.alloc(F * P * 4 * 4);
@@ -611,6 +618,7 @@ int kfn_eval_sequences(kfn_handle* h, const uint8_t* images, int S, int T, const
   // 1. measurement system + feature tower: frame-parallel over all S*T frames
   for (int64_t f0 = 0; f0 < F; f0 += frames_per_batch) {
     const int B = (int)((F - f0) < frames_per_batch ? (F - f0) : frames_per_batch);
+    if (batch_ready) KFN_CUDA_OK(cudaStreamWaitEvent(st, batch_ready[f0 / frames_per_batch], 0));
     // both networks start from the same preprocessed input (im2col rows / fp32 image): build it once per batch
     Arena a(sub, sub_bytes);
     const int64_t px = (int64_t)B * h->H * h->W;
@@ -639,6 +647,53 @@ int kfn_eval_sequences(kfn_handle* h, const uint8_t* images, int S, int T, const
   const int period = reinit_period > 0 ? reinit_period : (1 << 30);
   return launch_kalman_scan(measure, flow, sigw, nullptr, nullptr, transform, S, T, h->GH, h->GW, 0, period, nis_gate,
                             out_map, nullptr, nullptr, nullptr, nullptr, st);
+}
+}  // namespace
+
+extern "C" {
+
+int kfn_eval_sequences(kfn_handle* h, const uint8_t* images, int S, int T, const float* transform, int reinit_period,
+                       int nis_gate, int frames_per_batch, int pairs_per_batch, float* out_map, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  KFN_READY(h);
+  KFN_REQUIRE(images && transform && out_map && workspace, "null argument");
+  KFN_REQUIRE(S > 0 && T > 0 && frames_per_batch > 0 && pairs_per_batch > 0, "empty problem");
+  return eval_sequences_impl(h, images, S, T, transform, reinit_period, nis_gate, frames_per_batch, pairs_per_batch, out_map,
+                             workspace, workspace_bytes, (cudaStream_t)stream, nullptr);
+}
+
+int kfn_eval_sequences_host(kfn_handle* h, const uint8_t* host_images, int S, int T, const float* transform,
+                            int reinit_period, int nis_gate, int frames_per_batch, int pairs_per_batch, float* host_out,
+                            uint8_t* dev_images, float* dev_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  KFN_READY(h);
+  KFN_REQUIRE(host_images && host_out && dev_images && dev_out && transform && workspace, "null argument");
+  KFN_REQUIRE(S > 0 && T > 0 && frames_per_batch > 0 && pairs_per_batch > 0, "empty problem");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t F = (int64_t)S * T, img_bytes = (int64_t)h->H * h->W * 3;
+  const int nb = (int)((F + frames_per_batch - 1) / frames_per_batch);
+  if (!h->copy_stream) KFN_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  if (!h->compute_done) KFN_CUDA_OK(cudaEventCreateWithFlags(&h->compute_done, cudaEventDisableTiming));
+  while ((int)h->copy_events.size() < nb) {
+    cudaEvent_t e;
+    KFN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->copy_events.push_back(e);
+  }
+  // the staging buffer may still be read by work already queued on `st` (previous call): order the copies after it
+  KFN_CUDA_OK(cudaEventRecord(h->compute_done, st));
+  KFN_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->compute_done, 0));
+  for (int b = 0; b < nb; ++b) {
+    const int64_t f0 = (int64_t)b * frames_per_batch;
+    const int64_t nfr = (F - f0) < frames_per_batch ? (F - f0) : frames_per_batch;
+    KFN_CUDA_OK(cudaMemcpyAsync(dev_images + f0 * img_bytes, host_images + f0 * img_bytes, (size_t)(nfr * img_bytes),
+                                cudaMemcpyHostToDevice, h->copy_stream));
+    KFN_CUDA_OK(cudaEventRecord(h->copy_events[b], h->copy_stream));
+  }
+  int rc = eval_sequences_impl(h, dev_images, S, T, transform, reinit_period, nis_gate, frames_per_batch, pairs_per_batch,
+                               dev_out, workspace, workspace_bytes, st, h->copy_events.data());
+  if (rc != KFN_OK) return rc;
+  KFN_CUDA_OK(cudaMemcpyAsync(host_out, dev_out, (size_t)(F * h->GH * h->GW * 4 * sizeof(float)), cudaMemcpyDeviceToHost, st));
+  KFN_CUDA_OK(cudaStreamSynchronize(st));
+  return KFN_OK;
 }
 
 int kfn_conv_layer(kfn_handle* h, const char* op_key, const void* in, int N, int IH, int IW, int in_cs, void* out, int OH,

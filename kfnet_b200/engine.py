@@ -82,6 +82,30 @@ class Engine:
         _lib.check(self.lib.kfn_scoordnet_forward(self.h, _ptr(images), B, _ptr(out), _ptr(ws), ws.numel(), self._stream()))
         return out
 
+    # ---- end to end from HOST memory through the C ABI (kfn_eval_sequences_host): pinned uint8 frames in, pinned maps out ----
+    def eval_sequences_host(self, host_images, transform, host_out=None, reinit_period=500, nis_gate=False,
+                            frames_per_batch=8, pairs_per_batch=4):
+        assert host_images.dim() == 5 and host_images.dtype == torch.uint8 and not host_images.is_cuda and host_images.is_contiguous()
+        S, T = host_images.shape[:2]
+        assert tuple(host_images.shape[-3:]) == (self.H, self.W, 3)
+        if host_out is None:
+            host_out = torch.empty(S, T, self.GH, self.GW, 4, dtype=torch.float32).pin_memory()
+        key = (S, T)
+        if getattr(self, "_host_stage_key", None) != key:
+            self._host_stage = (torch.empty(S, T, self.H, self.W, 3, dtype=torch.uint8, device=self._dev()),
+                                torch.empty(S, T, self.GH, self.GW, 4, dtype=torch.float32, device=self._dev()))
+            self._host_stage_key = key
+        dev_imgs, dev_out = self._host_stage
+        Tm = np.ascontiguousarray(np.asarray(transform, dtype=np.float32).reshape(16))
+        need = (self.lib.kfn_workspace_bytes(self.h, frames_per_batch, pairs_per_batch)
+                + self.lib.kfn_sequence_extra_bytes(self.h, S, T))
+        ws = self._workspace(need)
+        _lib.check(self.lib.kfn_eval_sequences_host(self.h, C.c_void_p(host_images.data_ptr()), S, T, Tm.ctypes.data_as(C.c_void_p),
+                                                    int(reinit_period), 1 if nis_gate else 0, int(frames_per_batch),
+                                                    int(pairs_per_batch), C.c_void_p(host_out.data_ptr()), _ptr(dev_imgs),
+                                                    _ptr(dev_out), _ptr(ws), ws.numel(), self._stream()))
+        return host_out
+
     # ---- the same, replayed from a CUDA graph (captured on first use for a given set of buffers / parameters):
     #      removes the CPU launch cost and most of the inter-kernel gaps of the ~7000 launches of a 256-frame step ----
     def eval_sequences_graphed(self, images, transform, out, reinit_period=500, nis_gate=False, frames_per_batch=8,

@@ -74,3 +74,16 @@ def test_graph_replay_and_batching_are_bit_identical(staged):
     two = torch.cat([seq, seq]).contiguous()                                              # S = 2 identical sequences
     b = eng.eval_sequences(two, Tm, reinit_period=500, frames_per_batch=7, pairs_per_batch=3)
     assert torch.equal(b[0], a[0]) and torch.equal(b[1], a[0])
+
+
+def test_host_buffer_entry_point_matches_device_path(staged):
+    """kfn_eval_sequences_host (pinned host frames in, pinned host maps out, batch-wise H2D on the library's copy stream)
+    == kfn_eval_sequences on device-resident frames, bit for bit; repeated calls reuse the staging buffers safely."""
+    eng, imgs, _, _, _, _ = staged
+    Tm = cases.transform().astype(np.float32)
+    seq = imgs.unsqueeze(0).contiguous()
+    ref = eng.eval_sequences(seq, Tm, reinit_period=500, frames_per_batch=5, pairs_per_batch=4).cpu()
+    host = seq.cpu().pin_memory()
+    for _ in range(3):
+        out = eng.eval_sequences_host(host, Tm, reinit_period=500, frames_per_batch=5, pairs_per_batch=4)
+        assert torch.equal(out, ref)
