@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
-for cfg in "16 16" "16 32" "32 16" "32 32" "16 8" "64 32"; do
+for cfg in "16 16" "8 8" "32 16" "16 32"; do
   set -- $cfg
   python bench.py --steps 2 --warmup 2 --cpu_frames 0 --frames_per_batch $1 --pairs_per_batch $2 2>/dev/null | python -c "
 import json,sys
