@@ -136,6 +136,15 @@ KFN_API int kfn_flow_warp_kalman(const float* flow, const float* sigma_w, const 
                          const float* transform, int GH, int GW, float* temp, float* kf, float* nis,
                          float* out_map, int32_t* taps, void* stream);
 
+/* Stand-alone bilinear sampler (tools/util.py:3-94; fused into kfn_kalman_scan on the hot path): imgs device fp32
+ * [N,H,W,C], coords device fp32 [N,Ht,Wt,2] = (x, y) in source pixels, out device fp32 [N,Ht,Wt,C]. */
+KFN_API int kfn_bilinear_sampler(const float* imgs, const float* coords, float* out, int N, int H, int W, int C, int Ht, int Wt,
+                         void* stream);
+
+/* Stand-alone rigid transform of a coordinate map (KFNet/util.py:12-40, ApplyTransform): in/out device fp32 [npix,3],
+ * transform HOST fp32 [16] row-major 4x4 (fused into kfn_kalman_scan's output on the hot path). */
+KFN_API int kfn_apply_transform(const float* in, float* out, int64_t npix, const float* transform, void* stream);
+
 /* Pointwise Kalman update and NIS on already-aligned maps (no warp): KFNet.BuildKFCoord (KFNet.py:148-162) and
  * KFNet.GetNIS (:164-184).  prior = (last/temp coord xyz, uncertainty), measure = (measure coord xyz, sigma_z):
  * device fp32 [npix,4]; posterior [npix,4] and/or nis [npix,3] (either may be NULL). */

@@ -25,6 +25,8 @@ SIGNATURES = {
     "kfn_oflownet_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "kfn_kalman_scan": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kfn_flow_warp_kalman": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kfn_bilinear_sampler": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "kfn_apply_transform": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "kfn_kalman_update": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "kfn_sequence_extra_bytes": (_i64, [_vp, _i, _i]),
     "kfn_eval_sequences": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),

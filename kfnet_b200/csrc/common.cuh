@@ -86,6 +86,9 @@ int launch_kalman_scan(const float* measure, const float* flow, const float* sig
                        float* state_out, const float* T16_host, int S, int T, int GH, int GW, int first_index,
                        int reinit_period, int nis_gate, float* out_map, float* temp, float* kf, float* nis,
                        int32_t* taps, cudaStream_t st);
+int launch_bilinear_sampler(const float* imgs, const float* coords, float* out, int N, int H, int W, int C, int Ht, int Wt,
+                            cudaStream_t st);
+int launch_apply_transform(const float* in, float* out, int64_t npix, const float* T16_host, cudaStream_t st);
 int launch_kalman_update(const float* prior, const float* meas, int64_t npix, float* post, float* nis, cudaStream_t st);
 
 }  // namespace kfn

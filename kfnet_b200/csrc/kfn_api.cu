@@ -585,6 +585,17 @@ int kfn_flow_warp_kalman(const float* flow, const float* sigma_w, const float* l
                             nis, taps, (cudaStream_t)stream);
 }
 
+int kfn_bilinear_sampler(const float* imgs, const float* coords, float* out, int N, int H, int W, int C, int Ht, int Wt,
+                         void* stream) {
+  KFN_REQUIRE(imgs && coords && out && N > 0 && H > 0 && W > 0 && C > 0 && Ht > 0 && Wt > 0, "null/empty argument");
+  return launch_bilinear_sampler(imgs, coords, out, N, H, W, C, Ht, Wt, (cudaStream_t)stream);
+}
+
+int kfn_apply_transform(const float* in, float* out, int64_t npix, const float* transform, void* stream) {
+  KFN_REQUIRE(in && out && transform && npix > 0, "null/empty argument");
+  return launch_apply_transform(in, out, npix, transform, (cudaStream_t)stream);
+}
+
 int kfn_kalman_update(const float* prior, const float* measure, int64_t npix, float* posterior, float* nis, void* stream) {
   KFN_REQUIRE(prior && measure && npix > 0 && (posterior || nis), "null/empty argument");
   return launch_kalman_update(prior, measure, npix, posterior, nis, (cudaStream_t)stream);

@@ -530,4 +530,54 @@ int launch_kalman_update(const float* prior, const float* meas, int64_t npix, fl
   return KFN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stand-alone tools/util.py:bilinear_sampler (3-94): imgs [N,H,W,C] sampled at coords [N,Ht,Wt,2] (x,y) -> [N,Ht,Wt,C],
+// with the reference's clipped-neighbour weights (:56-59) and add_n order (:90-93).  One thread per output element.
+__global__ void bilinear_sampler_kernel(const float* __restrict__ imgs, const float* __restrict__ coords,
+                                        float* __restrict__ out, int N, int H, int W, int C, int Ht, int Wt) {
+  const int64_t total = (int64_t)N * Ht * Wt * C;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int64_t pt = i / C;                       // (n, yt, xt)
+  const int n = (int)(pt / ((int64_t)Ht * Wt));
+  const float cx = coords[pt * 2 + 0], cy = coords[pt * 2 + 1];
+  const float xmax = (float)(W - 1), ymax = (float)(H - 1);
+  const float x0 = floorf(cx), y0 = floorf(cy);
+  const float x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+  const float x0s = fminf(fmaxf(x0, 0.f), xmax), x1s = fminf(fmaxf(x1, 0.f), xmax);
+  const float y0s = fminf(fmaxf(y0, 0.f), ymax), y1s = fminf(fmaxf(y1, 0.f), ymax);
+  const float wx0 = x1s - cx, wx1 = cx - x0s, wy0 = y1s - cy, wy1 = cy - y0s;
+  const float* base = imgs + (int64_t)n * H * W * C + c;
+  const float i00 = base[((int64_t)y0s * W + (int64_t)x0s) * C], i01 = base[((int64_t)y1s * W + (int64_t)x0s) * C];
+  const float i10 = base[((int64_t)y0s * W + (int64_t)x1s) * C], i11 = base[((int64_t)y1s * W + (int64_t)x1s) * C];
+  out[i] = (((wx0 * wy0) * i00 + (wx0 * wy1) * i01) + (wx1 * wy0) * i10) + (wx1 * wy1) * i11;
+}
+
+int launch_bilinear_sampler(const float* imgs, const float* coords, float* out, int N, int H, int W, int C, int Ht, int Wt,
+                            cudaStream_t st) {
+  const int64_t total = (int64_t)N * Ht * Wt * C;
+  bilinear_sampler_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(imgs, coords, out, N, H, W, C, Ht, Wt);
+  KFN_LAUNCH_OK();
+  return KFN_OK;
+}
+
+// Stand-alone KFNet/util.py:ApplyTransform (12-40): (T @ [x,y,z,1])[:3] for every pixel of a [npix,3] map.
+__global__ void apply_transform_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t npix, Xform X) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const float x = in[i * 3 + 0], y = in[i * 3 + 1], z = in[i * 3 + 2];
+  out[i * 3 + 0] = ((X.m[0] * x + X.m[1] * y) + X.m[2] * z) + X.m[3];
+  out[i * 3 + 1] = ((X.m[4] * x + X.m[5] * y) + X.m[6] * z) + X.m[7];
+  out[i * 3 + 2] = ((X.m[8] * x + X.m[9] * y) + X.m[10] * z) + X.m[11];
+}
+
+int launch_apply_transform(const float* in, float* out, int64_t npix, const float* T16_host, cudaStream_t st) {
+  Xform X;
+  for (int i = 0; i < 16; ++i) X.m[i] = T16_host[i];
+  apply_transform_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(in, out, npix, X);
+  KFN_LAUNCH_OK();
+  return KFN_OK;
+}
+
 }  // namespace kfn

@@ -133,3 +133,18 @@ def test_kalman_update_and_nis_pointwise(eng):
     assert_close_rms(post.cpu(), torch.cat([kc, ku], -1), 2e-6, "posterior")
     assert_close_rms(nis.cpu(), O.get_nis(meas[..., :3], meas[..., 3:4], prior[..., :3], prior[..., 3:4]), 2e-6, "nis")
     assert bool((post[..., 3].cpu() <= prior[..., 3] + 1e-7).all())                 # sigma+ <= sigma-
+
+
+def test_standalone_sampler_and_transform_vs_reference_golden(golden):
+    """kfn_bilinear_sampler / kfn_apply_transform (mirrors of tools/util.py:bilinear_sampler, KFNet/util.py:ApplyTransform)
+    against the vectors produced by running the reference's own functions on the TF1 shim."""
+    from kfnet_b200 import util as U
+    imgs, coords = cases.bilinear_case()
+    out = U.bilinear_sampler(torch.tensor(imgs, dtype=torch.float32).cuda(), torch.tensor(coords, dtype=torch.float32).cuda())
+    assert_close_rms(out.cpu(), golden["bilinear_out"], 5e-6, "bilinear_sampler incl. edge behaviour")
+    kc = torch.tensor(golden["full_rec_kf_coord"], dtype=torch.float32).cuda()
+    tr = U.ApplyTransform(kc, cases.transform())
+    assert_close_rms(tr.cpu(), golden["full_rec_trans_kf_coord"], 2e-6, "ApplyTransform")
+    pm = U.GetPixelMap(2, 3, 4)
+    assert pm.shape == (2, 3, 4, 2) and pm[0, 2, 3].tolist() == [3.0, 2.0]
+    assert U.HomoCoord(kc).shape[-1] == 4
