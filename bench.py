@@ -10,8 +10,9 @@ accumulate.  One step = one pass of the whole path over the rank's sequence.  N 
 sequences (weak scaling) + one NCCL all_gather of the per-rank output maps inside the timed step.
 
   value : frames/s with the uint8 images already resident in HBM (CUDA events, max over ranks)
-  e2e   : same metric through the public API with HOST (pinned) buffers: H2D of the images and D2H of the
-          [T,60,80,4] output maps inside the timed region, every step
+  e2e   : same metric through ONE C-ABI call per step with HOST (pinned) buffers (kfn_eval_sequences_host): H2D of the
+          images (streamed batch by batch inside the call), the whole path and the D2H of the [T,60,80,4] output maps
+          inside the timed region, every step; `e2e_pipelined` additionally overlaps the H2D of step i+1 with step i
   --impl reference : the reference's own per-frame eval loop (batch-of-2 SCoordNet+tower recomputation
           included, KFNet/eval.py:41,77-104) restated op-for-op on torch-CPU (oracle/), timed on the host cores.
           TensorFlow 1.13 cannot be installed offline, so this is kind="port".
