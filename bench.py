@@ -317,7 +317,7 @@ def run_ours(args):
             "e2e_pipelined": {"value": frames_total / (ms_e2e_pipe / 1e3), "unit": "frames/s",
                               "api": "Engine.eval_sequences_graphed + double-buffered H2D across steps (CUDA graph replay)"},
             "gpu_launches": int(launches * args.steps),
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel over the SCoordNet stack (%d launches per batch of %d frames incl. 1 im2col; 63 %% of the step)" % (n_sc, B),
+            "roofline": {"bound": "tensor", "kernel": "conv_tc kernels over the SCoordNet stack (%d launches per batch of %d frames, first layer reads the u8 frames; ~60 %% of the step)" % (n_sc, B),
                          "achieved": tf_ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf_ach / pk["tf_sustained"],
                          "peak_source": pk["src"] + " bf16 sustained", "traffic": None},
             "roofline_dominant_launch": roof_launch,

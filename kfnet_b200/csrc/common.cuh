@@ -67,6 +67,9 @@ struct ConvGeom {
   // dual output (tensor-core path): columns >= split_col go to a second NHWC tensor `out2` (channel stride out2_cs,
   // channels from 0) at the same pixel -- lets two layers that read the same input share one GEMM (conv1a + feat1).
   int split_col, out2_cs;
+  // fused first layer (tensor-core path, BF16 mode): `in` is the u8 NHWC image [N, IH, IW, 3]; the K = 32 operand row
+  // (27 window values - 128, zero padded) is built inside the kernel.  Cin = 32, one tap, stride 1.
+  int im2col_u8;
 };
 enum { EPI_NONE = 0, EPI_EXP_CH3 = 1, EPI_L2NORM = 2 };
 

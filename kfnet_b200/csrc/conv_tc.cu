@@ -13,9 +13,13 @@
 //   accumulators live in TMEM (2 stages, allocated by need), drained by 8 epilogue warps with tcgen05.ld while the
 //   next tile's MMAs run; bias + ReLU (+ exp / l2-normalise / limb split / conv2d_transpose phase scatter) fused.
 //
-// One persistent CTA (or two co-resident ones for small layers) per SM, 320 threads: warp 0 = TMA producer,
+// One persistent CTA (or two / three co-resident ones for small layers) per SM, 320 threads: warp 0 = TMA producer,
 // warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; the two warps of a
-// quadrant split the column blocks).  DESIGN.md section 4.1 has the measurements behind each design choice.
+// quadrant split the column blocks).  WIDE variant (576 threads) for one-CTA layers whose tiles carry few MMAs
+// (conv1a, conv1b): four accumulator stages and four epilogue groups of 4 warps, group g draining every 4th tile
+// whole -- the per-tile epilogue is a ~350-instruction dependent chain (profiles/r01h: 3100 cycles per tile against
+// 1700 cycles of MMAs), so four tiles are drained concurrently instead of one.
+// DESIGN.md section 4.1 has the measurements behind each design choice.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -32,7 +36,9 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kMaxStages = 12;
 constexpr int kThreads = 320;                           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kThreadsWide = 576;                       // WIDE: warps 2..17 = four epilogue groups
 constexpr int kEpiWarps = 8;
+constexpr int kMaxAcc = 4;                              // TMEM accumulator stages (2, or 4 in WIDE mode)
 constexpr uint32_t kEpiStageBytes = kEpiWarps * 2048;     // per epilogue warp: 32 rows x 64 B staging for coalesced stores
 constexpr long long kWatchdogCycles = 4000000000ll;   // ~2 s at 1.9 GHz: trap instead of hanging the GPU
 
@@ -61,7 +67,9 @@ struct __align__(8) TcParams {
   int pf_dist;                  // L2 prefetch distance in tiles (0 = off)
   // bf16x3: k-chunks = n_terms x cpk; term t multiplies A limb la[t] with W limb lw[t]
   int n_terms, cpk, in_ls, w_cin, out_limbs, out_ls;
-  int epi_warps;                // 8 (320-thread CTA) or 4 (192-thread CTA, three CTAs per SM)
+  int epi_warps;                // 8 (320-thread CTA), 4 (192-thread CTA, three CTAs per SM) or 16 (576-thread WIDE CTA)
+  int lg_groups;                // WIDE: log2 of the number of 4-warp epilogue groups (tile j -> group j % G); -1 = column split
+  int lg_acc;                   // log2 of the number of TMEM accumulator stages (1, or 2 in WIDE mode)
   uint32_t tmem_cols, acc_stride;   // TMEM columns allocated by this CTA (power of 2 >= 32) and columns per accumulator stage
   int phase_cout;               // merged conv2d_transpose phases (see ConvGeom)
   int split_col, out2_cs;       // dual output: columns >= split_col -> out2 (bf16, generic 16-column path)
@@ -69,6 +77,12 @@ struct __align__(8) TcParams {
   int x3acc;                    // 1: four 128-column TMEM accumulators (3 main-term splits + corrections), single-buffered
   int la[6], lw[6];
   uint32_t epi_stage_off;       // byte offset (from the 1024-aligned smem base) of the epilogue staging area
+  // fused first layer (BF16 mode): the A tile is the 32-wide im2col row of the 3x3x3 window, built in shared memory by
+  // four producer warps straight from the u8 image (SCoordNet.py:34-37 preprocess: u8 - 128 is exact in bf16, the
+  // 0.00625 scale is folded into the packed weights; taps outside the image are 0 = SAME padding of the preprocessed
+  // tensor); the [BN x 32] weight tile is resident.  No im2col tensor ever exists in HBM.
+  int im2col;
+  const uint8_t* img;
   uint32_t tap_off16[9];        // halo: ((1+dy) * 10*bn + (1+dx)) * row_bytes / 16 per tap
 };
 
@@ -204,8 +218,8 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint32_t smem_base, 
   uint64_t adesc = a0;
   TileIter it;
   for (it.init(p, total_tiles); it.valid(); it.next(p), ++j) {
-    const int a = j & 1;
-    const uint32_t aph = (uint32_t)(j >> 1) & 1u;
+    const int a = j & ((1 << p.lg_acc) - 1);
+    const uint32_t aph = (uint32_t)(j >> p.lg_acc) & 1u;
     mbar_wait(smem_u32(&s_tempty[a]), aph ^ 1u);
     tc_fence_after();
     const uint32_t tmem_d = tmem_base + (uint32_t)a * p.acc_stride;
@@ -238,8 +252,8 @@ __device__ __forceinline__ void mma_role_halo(const TcParams& p, uint32_t smem_b
   uint64_t adesc = a0;
   TileIter it;
   for (it.init(p, total_tiles); it.valid(); it.next(p), ++j) {
-    const int a = j & 1;
-    const uint32_t aph = (uint32_t)(j >> 1) & 1u;
+    const int a = j & ((1 << p.lg_acc) - 1);
+    const uint32_t aph = (uint32_t)(j >> p.lg_acc) & 1u;
     mbar_wait(smem_u32(&s_tempty[a]), aph ^ 1u);
     tc_fence_after();
     const uint32_t tmem_d = tmem_base + (uint32_t)a * p.acc_stride;
@@ -259,6 +273,34 @@ __device__ __forceinline__ void mma_role_halo(const TcParams& p, uint32_t smem_b
       if (++s == p.stages) { s = 0; ph ^= 1u; adesc = a0; }
     }
     umma_commit(smem_u32(&s_tfull[a]));
+  }
+}
+
+// fused first layer: one k-block per tile, A written by the im2col producer warps, B resident at the smem base
+template <int KSTEPS>
+__device__ __forceinline__ void mma_role_im2col(const TcParams& p, uint32_t smem_base, uint32_t tmem_base, int total_tiles,
+                                                uint64_t* s_full, uint64_t* s_empty, uint64_t* s_tfull, uint64_t* s_tempty,
+                                                uint64_t* s_wbar) {
+  mbar_wait(smem_u32(s_wbar), 0);               // resident weights have landed
+  const uint64_t desc_fixed = ((uint64_t)p.desc_hi << 32) | (1ull << 16);
+  const uint64_t stage16 = (uint64_t)(p.stage_bytes >> 4);
+  const uint64_t a0 = desc_fixed | (uint64_t)((smem_base + p.w_bytes_total) >> 4);
+  const uint64_t bdesc = desc_fixed | (uint64_t)(smem_base >> 4);
+  int s = 0, j = 0;
+  uint32_t ph = 0;
+  uint64_t adesc = a0;
+  TileIter it;
+  for (it.init(p, total_tiles); it.valid(); it.next(p), ++j) {
+    const int a = j & ((1 << p.lg_acc) - 1);
+    const uint32_t aph = (uint32_t)(j >> p.lg_acc) & 1u;
+    mbar_wait(smem_u32(&s_tempty[a]), aph ^ 1u);
+    mbar_wait(smem_u32(&s_full[s]), ph);
+    tc_fence_after();
+    umma_kblock<KSTEPS>(tmem_base + (uint32_t)a * p.acc_stride, adesc, bdesc, p.idesc, 0u);
+    umma_commit(smem_u32(&s_empty[s]));
+    umma_commit(smem_u32(&s_tfull[a]));
+    adesc += stage16;
+    if (++s == p.stages) { s = 0; ph ^= 1u; adesc = a0; }
   }
 }
 
@@ -301,12 +343,22 @@ __device__ __forceinline__ void mma_role_x3(const TcParams& p, uint32_t smem_bas
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
+// kLean (WIDE / fused-first-layer kernels): plain bf16 layers only -- the bf16x3 accumulator splits, limb outputs,
+// conv2d_transpose phase scatter and special epilogues are compiled out, which shortens the per-tile epilogue chain
+// these layers are bound by and frees registers for the 576 / 672-thread CTAs.
+template <bool kLean, bool kFirst>
 __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
+  const int f_x3acc = kLean ? 0 : p.x3acc;
+  const int f_out_limbs = kLean ? 1 : p.out_limbs;
+  const int f_out_ls = kLean ? 0 : p.out_ls;
+  const int f_phase_cout = kLean ? 0 : p.phase_cout;
+  const int f_epi = kLean ? (int)EPI_NONE : p.epi;
+  const bool f_im2col = kFirst && p.im2col;     // the im2col producer exists only in conv_tc_kernel_first
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full[kMaxStages];
   __shared__ __align__(8) uint64_t s_empty[kMaxStages];
-  __shared__ __align__(8) uint64_t s_tfull[2];
-  __shared__ __align__(8) uint64_t s_tempty[2];
+  __shared__ __align__(8) uint64_t s_tfull[kMaxAcc];
+  __shared__ __align__(8) uint64_t s_tempty[kMaxAcc];
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(8) uint64_t s_wbar;
 
@@ -319,12 +371,12 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_full[s]), f_im2col ? 4u : 1u);   // im2col: one arrival per producer warp
       mbar_init(smem_u32(&s_empty[s]), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < kMaxAcc; ++a) {
       mbar_init(smem_u32(&s_tfull[a]), 1);
-      mbar_init(smem_u32(&s_tempty[a]), (uint32_t)p.epi_warps);
+      mbar_init(smem_u32(&s_tempty[a]), p.lg_groups >= 0 ? 4u : (uint32_t)p.epi_warps);   // the warps draining one tile
     }
     mbar_init(smem_u32(&s_wbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -352,7 +404,59 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
   const int total_tiles = m_tiles * p.n_tiles;
   const int kblocks = p.ntaps * p.kchunks;
 
-  if (warp == 0) {
+  const bool extra_producer = f_im2col && warp >= 2 + p.epi_warps;   // im2col: three more producer warps after the epilogue's
+  if (f_im2col && (warp == 0 || extra_producer)) {
+    // ===================================================================== im2col producers (4 warps, one pixel per lane)
+    const int pq = warp == 0 ? 0 : warp - (1 + p.epi_warps);
+    if (pq == 0 && lane == 0) {
+      const uint32_t wbar = smem_u32(&s_wbar);
+      mbar_expect_tx(wbar, p.b_bytes);
+      tma_load_3d(smem_base, &tmB, wbar, 0, 0, 0);
+    }
+    const int r = pq * 32 + lane;                               // A-tile row = pixel of the tile, ordered [n][h][w]
+    const int r_wi = r & ((1 << p.lbw) - 1);
+    const int r_hi = (r >> p.lbw) & ((1 << p.lbh) - 1);
+    const int r_ni = r >> (p.lbw + p.lbh);
+    // 64-byte rows in the 64B-swizzled K-major layout TMA would produce: 16-byte chunk q of row r sits at chunk
+    // q ^ ((address >> 7) & 3) = q ^ ((r >> 1) & 3)  (stage bases are 1024-aligned)
+    uint8_t* const row_ptr = smem_raw + (smem_base - smem_u32(smem_raw)) + p.w_bytes_total + (uint32_t)r * 64u;
+    const int sw = (r >> 1) & 3;
+    const int H = p.MH, W = p.MW;
+    int s = 0;
+    uint32_t ph = 0;
+    TileIter it;
+    for (it.init(p, total_tiles); it.valid(); it.next(p)) {
+      const int x = (it.tw << p.lbw) + r_wi, y = (it.th << p.lbh) + r_hi, n = (it.tn << (7 - p.lbw - p.lbh)) + r_ni;
+      float e[32];
+#pragma unroll
+      for (int k = 27; k < 32; ++k) e[k] = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        const bool rowv = n < p.N && yy >= 0 && yy < H;
+        const uint8_t* src = p.img + (((int64_t)n * H + yy) * W + (x - 1)) * 3;
+#pragma unroll
+        for (int jj = 0; jj < 9; ++jj) {
+          const int xx = x - 1 + jj / 3;
+          const bool v = rowv && xx >= 0 && xx < W;
+          e[ky * 9 + jj] = v ? (float)__ldg(src + jj) - 128.0f : 0.f;
+        }
+      }
+      uint4 c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        c[q] = make_uint4(pack_bf16(e[8 * q], e[8 * q + 1]), pack_bf16(e[8 * q + 2], e[8 * q + 3]),
+                          pack_bf16(e[8 * q + 4], e[8 * q + 5]), pack_bf16(e[8 * q + 6], e[8 * q + 7]));
+      mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);             // the MMAs that read this stage have retired
+      uint8_t* dst = row_ptr + (uint32_t)s * p.stage_bytes;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(dst + ((q ^ sw) << 4)) = c[q];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_full[s]));
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 0) {
     // ===================================================================== TMA producer (one lane)
     if (lane == 0 && p.halo) {
       // resident weights: every (tap, chunk) tile once, one barrier
@@ -427,7 +531,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
     // ===================================================================== MMA issuer (one lane)
     if (lane == 0) {
       const int ksteps = p.KC >> 4;
-      if (p.x3acc) {
+      if (f_im2col) {
+        mma_role_im2col<2>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
+      } else if (f_x3acc) {
         if (ksteps == 4) mma_role_x3<4>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty);
         else if (ksteps == 2) mma_role_x3<2>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty);
         else mma_role_x3<1>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty);
@@ -445,13 +551,16 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
     // ===================================================================== epilogue (8 warps)
     // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the column blocks.
     const int quad = warp & 3;
-    const int hsel = (warp - 2) >> 2;
+    const bool grouped = p.lg_groups >= 0;                       // WIDE: 4-warp groups, each draining whole tiles
+    const int grp = grouped ? (warp - 2) >> 2 : 0;
+    const int hsel = grouped ? 0 : (warp - 2) >> 2;              // column split: which half of the column blocks
+    const bool col_split = !grouped && p.epi_warps == 8;
     const int row = quad * 32 + lane;
     const int bn_shift = p.halo ? p.lbn : (7 - p.lbw - p.lbh);
     const int esize = p.out_bf16 ? 2 : 4;
     // coalesced 32-column path: bf16 output, no special epilogue, 16-byte aligned rows / channel offsets
-    const bool fast32 = p.out_bf16 && p.epi == EPI_NONE && ((p.out_cs * 2) & 15) == 0 && ((p.out_coff * 2) & 15) == 0 &&
-                        ((p.out_ls * 2) & 15) == 0 &&
+    const bool fast32 = p.out_bf16 && f_epi == EPI_NONE && ((p.out_cs * 2) & 15) == 0 && ((p.out_coff * 2) & 15) == 0 &&
+                        ((f_out_ls * 2) & 15) == 0 &&
                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_stage_off + (uint32_t)(warp - 2) * 2048u;
     // tile-invariant part of every row's output offset (bytes): computed once per thread.
@@ -474,6 +583,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
     int j = 0;
     TileIter it;
     for (it.init(p, total_tiles); it.valid(); it.next(p), ++j) {
+      if (grouped && (j & ((1 << p.lg_groups) - 1)) != grp) continue;
       const int n0 = it.tn << bn_shift;
       const int64_t tile_off = ((((int64_t)n0 * p.OH + (it.th << p.lbh) * p.omul + p.oaddy) * p.OW +
                                  (it.tw << p.lbw) * p.omul + p.oaddx) * p.out_cs + p.out_coff) * esize;
@@ -485,15 +595,16 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
         const int64_t tile_pix = ((int64_t)n0 * p.OH + (it.th << p.lbh) * p.omul + p.oaddy) * p.OW + (it.tw << p.lbw) * p.omul + p.oaddx;
         orow2 = reinterpret_cast<uint8_t*>(p.out2) + tile_pix * p.out2_cs * 2 + my_off2;
       }
-      const int a = p.x3acc ? 0 : (j & 1);
-      const uint32_t aph = p.x3acc ? ((uint32_t)j & 1u) : ((uint32_t)(j >> 1) & 1u);
+      // accumulator stage of tile j = j % stages (WIDE: stages == groups, so group g always drains stage g)
+      const int a = f_x3acc ? 0 : (j & ((1 << p.lg_acc) - 1));
+      const uint32_t aph = f_x3acc ? ((uint32_t)j & 1u) : ((uint32_t)(j >> p.lg_acc) & 1u);
       mbar_wait(smem_u32(&s_tfull[a]), aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (p.x3acc ? 0u : (uint32_t)a * p.acc_stride);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (f_x3acc ? 0u : (uint32_t)a * p.acc_stride);
       const int col0 = it.nt * p.BN;
       const int n_main = p.ntaps < 3 ? p.ntaps : 3;     // x3acc: main-term accumulators in use
 
-      if (p.epi == EPI_L2NORM) {
+      if (f_epi == EPI_L2NORM) {
         if (hsel == 0) {
           // feat7: BN == Cout == 32, fp32 output, x * rsqrt(max(sum x^2, 1e-12))  (KFNet/KFNet.py:340)
           uint32_t r[32];
@@ -502,7 +613,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           float ss = 0.f;
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (p.x3acc) {
+          if (f_x3acc) {
             for (int acc = 1; acc < 4; ++acc) {
               if (acc < 3 && acc >= n_main) continue;
               tmem_ld32(taddr + (uint32_t)acc * p.acc_stride, r);
@@ -528,8 +639,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
 #pragma unroll
           for (int i = 0; i < 4; ++i) { wrow[i] = tile_ptr + wr_off[i]; wvalid[i] = n0 + wr_ni[i] < p.N; }
           const int fast_end = p.split_col ? p.split_col : p.Cout;
-          for (; nc + 32 <= p.BN && col0 + nc + 32 <= fast_end && (p.phase_cout == 0 || (p.phase_cout & 31) == 0); nc += 32) {
-            if (p.epi_warps == 8 && ((nc >> 5) & 1) != hsel) continue;
+          for (; nc + 32 <= p.BN && col0 + nc + 32 <= fast_end && (f_phase_cout == 0 || (f_phase_cout & 31) == 0); nc += 32) {
+            if (col_split && ((nc >> 5) & 1) != hsel) continue;
             uint32_t r[32];
             tmem_ld32(taddr + nc, r);
             const int c = col0 + nc;
@@ -537,15 +648,15 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
             // merged conv2d_transpose: this 32-column block belongs to phase ph -> pixel offset (py, px), channel cc
             int cc = c;
             int64_t ph_off = 0;
-            if (p.phase_cout) {
-              const int ph = c / p.phase_cout;
-              cc = c - ph * p.phase_cout;
+            if (!kLean && f_phase_cout) {
+              const int ph = c / (kLean ? 1 : f_phase_cout);
+              cc = c - ph * f_phase_cout;
               ph_off = ((int64_t)(ph >> 1) * p.OW + (ph & 1)) * p.out_cs * 2;
             }
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            if (p.x3acc) {   // main splits 1, 2 and the correction accumulator, added with RN fp32
+            if (f_x3acc) {   // main splits 1, 2 and the correction accumulator, added with RN fp32
               for (int acc = 1; acc < 4; ++acc) {
                 if (acc < 3 && acc >= n_main) continue;
                 tmem_ld32(taddr + (uint32_t)acc * p.acc_stride + nc, r);
@@ -562,7 +673,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            for (int l = 0; l < p.out_limbs; ++l) {
+            for (int l = 0; l < f_out_limbs; ++l) {
               // stage: row = lane (64 B), 16-byte chunk q at slot q ^ ((lane >> 1) & 3): conflict-free both ways
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -575,10 +686,10 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
               for (int i = 0; i < 4; ++i) {
                 const int rr = i * 8 + (lane >> 2);
                 const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((cq ^ ((rr >> 1) & 3)) << 4));
-                if (wvalid[i]) *reinterpret_cast<uint4*>(wrow[i] + ph_off + ((int64_t)cc + (int64_t)l * p.out_ls) * 2 + cq * 16) = val;
+                if (wvalid[i]) *reinterpret_cast<uint4*>(wrow[i] + ph_off + ((int64_t)cc + (int64_t)l * f_out_ls) * 2 + cq * 16) = val;
               }
               __syncwarp();
-              if (l + 1 < p.out_limbs) {     // next limb = residual after removing this limb's bf16 value
+              if (l + 1 < f_out_limbs) {     // next limb = residual after removing this limb's bf16 value
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] -= __bfloat162float(__float2bfloat16(v[i]));
               }
@@ -586,10 +697,10 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           }
         }
         for (; nc < p.BN; nc += 16) {
-          if (p.epi_warps == 8 && ((nc >> 4) & 1) != hsel) continue;
+          if (col_split && ((nc >> 4) & 1) != hsel) continue;
           float v[16];
           tmem_ld16(taddr + nc, v);
-          if (p.x3acc) {
+          if (f_x3acc) {
             for (int acc = 1; acc < 4; ++acc) {
               if (acc < 3 && acc >= n_main) continue;
               float w[16];
@@ -609,21 +720,21 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (p.epi == EPI_EXP_CH3 && c == 0) v[3] = expf(v[3]);
+          if (f_epi == EPI_EXP_CH3 && c == 0) v[3] = expf(v[3]);
           if (!valid) continue;
           const int nvalid = p.Cout - c;
           int cc = c;
           int64_t ph_off = 0;
-          if (p.phase_cout) {
-            const int ph = c / p.phase_cout;
-            cc = c - ph * p.phase_cout;
+          if (!kLean && f_phase_cout) {
+            const int ph = c / (kLean ? 1 : f_phase_cout);
+            cc = c - ph * f_phase_cout;
             ph_off = ((int64_t)(ph >> 1) * p.OW + (ph & 1)) * p.out_cs * esize;
           }
           if (p.out_bf16) {
             uint8_t* rowbase = orow;
             if (p.split_col && c >= p.split_col) { rowbase = orow2; cc = c - p.split_col; }
-            for (int l = 0; l < p.out_limbs; ++l) {
-              uint8_t* dst = rowbase + ph_off + ((int64_t)cc + (int64_t)l * p.out_ls) * 2;
+            for (int l = 0; l < f_out_limbs; ++l) {
+              uint8_t* dst = rowbase + ph_off + ((int64_t)cc + (int64_t)l * f_out_ls) * 2;
               if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                 uint4 o0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                 uint4 o1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
@@ -635,7 +746,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
                 for (int i = 0; i < 16; ++i)
                   if (i < nvalid) d[i] = __float2bfloat16(v[i]);
               }
-              if (l + 1 < p.out_limbs) {
+              if (l + 1 < f_out_limbs) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] -= __bfloat162float(__float2bfloat16(v[i]));
               }
@@ -671,11 +782,22 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
 // for the small latency-bound ones, so one CTA's barrier / TMA / TMEM latencies are covered by the other's work.
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  conv_tc_body(tmA, tmB, p);
+  conv_tc_body<false, false>(tmA, tmB, p);
 }
 __global__ void __launch_bounds__(kThreads, 2)
 conv_tc_kernel_x2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  conv_tc_body(tmA, tmB, p);
+  conv_tc_body<false, false>(tmA, tmB, p);
+}
+// WIDE: 16 epilogue warps (four groups draining four tiles concurrently) for one-CTA layers with short tiles.
+__global__ void __launch_bounds__(kThreadsWide, 1)
+conv_tc_kernel_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  conv_tc_body<true, false>(tmA, tmB, p);
+}
+
+// Fused first layer: WIDE (or the 320-thread layout) plus three more im2col producer warps.
+__global__ void __launch_bounds__(kThreadsWide + 96, 1)
+conv_tc_kernel_first(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  conv_tc_body<true, true>(tmA, tmB, p);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -713,6 +835,23 @@ bool tc_three_ctas_enabled() {
   static const bool on = [] { const char* e = getenv("KFN_TC_THREE_CTAS"); return !(e && e[0] == '0'); }();
   return on;
 }
+// variants awaiting their B200 validation run are opt-in (=1); validated ones are on unless =0
+bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? e[0] != '0' : dflt;
+}
+bool tc_wide_enabled() {
+  static const bool on = env_flag("KFN_TC_WIDE", false);
+  return on;
+}
+bool tc_group2_enabled() {
+  static const bool on = env_flag("KFN_TC_GROUP2", false);
+  return on;
+}
+bool tc_im2col_fused_enabled() {
+  static const bool on = env_flag("KFN_TC_IM2COL_FUSED", false);
+  return on;
+}
 bool tc_pdl_enabled() {
   static const bool on = [] { const char* e = getenv("KFN_TC_PDL"); return !(e && e[0] == '0'); }();
   return on;
@@ -732,8 +871,11 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   KFN_REQUIRE(g.in_cs % 8 == 0, "input channel stride must keep pixels 16-byte aligned");
   KFN_REQUIRE(CoutP % 16 == 0 && (CoutP <= 128 || CoutP % 128 == 0), "CoutP must be 16..128 (mult of 16) or k*128");
   KFN_REQUIRE(g.istride == 1 || (g.istride == 2 && g.IH % 2 == 0 && g.IW % 2 == 0), "stride must be 1 or 2 (even input)");
-  KFN_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
+  KFN_REQUIRE((g.im2col_u8 || (reinterpret_cast<uintptr_t>(in) & 15) == 0) && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
               "TMA needs 16-byte aligned global addresses");
+  if (g.im2col_u8)
+    KFN_REQUIRE(g.Cin == 32 && g.ntaps == 1 && g.istride == 1 && g.omul == 1 && g.limbs_w <= 1 && g.limbs_a <= 1 &&
+                CoutP <= 128 && g.IH == g.MH && g.IW == g.MW, "fused first layer shape");
   static_assert(sizeof(TcParams) + 2 * sizeof(CUtensorMap) <= sizeof(TcConvPlan::blob), "TcConvPlan blob too small");
 
   CUtensorMap* tmA = reinterpret_cast<CUtensorMap*>(plan->blob);
@@ -817,12 +959,39 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   p.tmem_cols = tmem_cols;
   const uint32_t stage_guess = ((uint32_t)(kBlockM + BN) * row_bytes + 1023u) & ~1023u;
   const bool streaming = g.ntaps == 1 && g.Cin / KC == 1 && (int64_t)g.N * g.MH * g.MW > (1 << 20);   // K=KC 1-tap GEMMs over big maps
-  const bool two_ctas = tc_two_ctas_enabled() && !streaming && tmem_cols <= 256 && (12u * stage_guess <= 88u * 1024u || BN <= 64);
+  const bool two_ctas = tc_two_ctas_enabled() && !streaming && !g.im2col_u8 && tmem_cols <= 256 && (12u * stage_guess <= 88u * 1024u || BN <= 64);
   // three CTAs/SM (192 threads, 4 epilogue warps, 56 KB pipeline) for the narrowest layers
   const bool three_ctas = two_ctas && tc_three_ctas_enabled() && tmem_cols <= 128 && 6u * stage_guess <= 56u * 1024u;
   plan->ctas_per_sm = three_ctas ? 3 : two_ctas ? 2 : 1;
   p.epi_warps = three_ctas ? 4 : 8;
-  const uint32_t budget = three_ctas ? 56 * 1024 : two_ctas ? 88 * 1024 : 200 * 1024;   // n x (budget + staging + 1 KB + static) fits the 228 KB SM
+  uint32_t budget = three_ctas ? 56 * 1024 : two_ctas ? 88 * 1024 : 200 * 1024;   // n x (budget + staging + 1 KB + static) fits the 228 KB SM
+  const uint32_t halo_stage = halo ? (((uint32_t)(10 * hbn * (hbh + 2) * row_bytes) + 1023u) & ~1023u) : 0u;
+  if (halo && w_total + 3 * halo_stage > budget) {   // a co-resident budget cannot hold resident weights + pipeline
+    plan->ctas_per_sm = 1; p.epi_warps = 8; budget = 200 * 1024;
+  }
+  // WIDE: a one-CTA layer whose tile carries so few MMA cycles that the ~3000-cycle epilogue chain of one tile would
+  // bound it (tensor time per MMA ~ max(BN/2, 48) cycles: N <= 64 is bound by the A-operand fetch from smem).
+  // Four accumulator stages of roundup(BN, 32) columns, four epilogue groups, 32 KB of store staging.
+  const int64_t mma_cycles = (int64_t)g.ntaps * (g.Cin / KC) * (KC / 16) * (BN / 2 > 48 ? BN / 2 : 48);
+  const bool lean_ok = !x3 && g.limbs_out <= 1 && g.phase_cout == 0 && g.epi == EPI_NONE;   // what conv_tc_body<true> keeps
+  if (g.im2col_u8) KFN_REQUIRE(lean_ok && plan->ctas_per_sm == 1, "fused first layer: plain bf16 layer, one CTA per SM");
+  const bool wide = tc_wide_enabled() && lean_ok && plan->ctas_per_sm == 1 && BN <= 128 && mma_cycles <= 2500 &&
+                    (int64_t)g.N * g.MH * g.MW >= (int64_t)kBlockM * 8 * num_sms;
+  p.lg_groups = -1; p.lg_acc = 1;
+  plan->threads = plan->ctas_per_sm == 3 ? 192 : kThreads;
+  if (wide) {
+    p.lg_groups = 2; p.lg_acc = 2; p.epi_warps = 16;
+    p.acc_stride = (uint32_t)(BN + 31) & ~31u;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 4u * p.acc_stride) p.tmem_cols <<= 1;
+    budget = 184 * 1024;
+    plan->threads = kThreadsWide;
+  } else if (tc_group2_enabled() && !x3 && plan->ctas_per_sm == 2 && g.epi != EPI_L2NORM) {
+    // co-resident pairs: the two 4-warp halves of the epilogue alternate tiles (each draining its own accumulator
+    // stage whole) instead of splitting one tile's column blocks -- the per-tile fixed cost is paid once per two tiles
+    // and layers with a single 32-column block keep all eight warps busy
+    p.lg_groups = 1;
+  }
   cuuint64_t dimA[5], strA[4];
   cuuint32_t boxA[5];
   if (halo) {
@@ -834,9 +1003,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     p.w_tile_bytes = w_tile_bytes; p.w_bytes_total = w_total;
     for (int t = 0; t < g.ntaps; ++t)
       p.tap_off16[t] = (uint32_t)(((1 + g.dy[t]) * 10 * hbn + (1 + g.dx[t])) * row_bytes) >> 4;
-    uint32_t hb = budget;
-    if (w_total + 3 * p.stage_bytes > hb) { hb = 200 * 1024; plan->ctas_per_sm = 1; p.epi_warps = 8; }
-    int stages = (int)((hb - w_total) / p.stage_bytes);
+    int stages = (int)((budget - w_total) / p.stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     KFN_REQUIRE(stages >= 2, "halo pipeline needs at least 2 stages");
     p.stages = stages;
@@ -854,11 +1021,18 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     p.tiles_w = g.MW / bw; p.tiles_h = g.MH / bh; p.tiles_n = (g.N + bn - 1) / bn;
     p.a_bytes = (uint32_t)(kBlockM * row_bytes);
     p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
-    int stages = (int)(budget / p.stage_bytes);
+    uint32_t resident = 0;
+    if (g.im2col_u8) {   // resident weight tile at the base, stages hold only the A tile the producer warps write
+      p.im2col = 1; p.img = reinterpret_cast<const uint8_t*>(in);
+      p.stage_bytes = p.a_bytes;
+      p.w_tile_bytes = w_tile_bytes; p.w_bytes_total = resident = w_tile_bytes;
+      plan->threads += 96;
+    }
+    int stages = (int)((budget - resident) / p.stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     KFN_REQUIRE(stages >= 2, "pipeline needs at least 2 stages");
     p.stages = stages;
-    p.epi_stage_off = (uint32_t)p.stages * p.stage_bytes;
+    p.epi_stage_off = resident + (uint32_t)p.stages * p.stage_bytes;
     plan->smem = (size_t)p.epi_stage_off + (size_t)p.epi_warps * 2048 + 1024;
     boxA[0] = (cuuint32_t)KC; boxA[1] = (cuuint32_t)bw; boxA[2] = 1u; boxA[3] = (cuuint32_t)bh; boxA[4] = (cuuint32_t)bn;
     if (g.istride == 1) {
@@ -869,9 +1043,10 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
       strA[0] = cs * 2; strA[1] = cs * g.IW; strA[2] = cs * g.IW * 2; strA[3] = cs * g.IW * g.IH;
     }
   }
-  CUresult r = encode(tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dimA, strA, boxA, ones,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  if (!g.im2col_u8)   // (the fused first layer has no activation tensor map: tmA stays a copy of tmB, never used)
+    r = encode(tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dimA, strA, boxA, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r)); return KFN_ERR_CUDA; }
   // ---- B: packed weights [tap][CoutP][Cin]
   cuuint64_t dimB[3] = {(cuuint64_t)g.Cin * limbs_w, (cuuint64_t)CoutP, (cuuint64_t)g.ntaps};
@@ -880,6 +1055,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   r = encode(tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dimB, strB, boxB, ones,
              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); return KFN_ERR_CUDA; }
+  if (g.im2col_u8) memcpy(tmA, tmB, sizeof(CUtensorMap));
 
   {
     // prefetch only for memory/latency-bound shapes (few k-blocks per tile); ~384 KB ahead per SM
@@ -905,6 +1081,9 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
     const int max_smem = 201 * 1024 + 1024 + (int)kEpiStageBytes;
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, 106 * 1024));
+    // WIDE: 184 KB pipeline + 32 KB staging + 1 KB alignment; first layer in the 320-thread layout: 200 + 16 + 1 KB
+    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_first, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     attr_set = true;
   }
   const CUtensorMap* tmA = reinterpret_cast<const CUtensorMap*>(plan.blob);
@@ -912,7 +1091,7 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)plan.grid);
-  cfg.blockDim = dim3(plan.ctas_per_sm == 3 ? 192 : kThreads);
+  cfg.blockDim = dim3((unsigned)plan.threads);
   cfg.dynamicSmemBytes = plan.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -920,7 +1099,11 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
-  if (plan.ctas_per_sm >= 2)
+  if (p.im2col)
+    KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_first, tmA[0], tmA[1], p));
+  else if (plan.threads == kThreadsWide)
+    KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_wide, tmA[0], tmA[1], p));
+  else if (plan.ctas_per_sm >= 2)
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_x2, tmA[0], tmA[1], p));
   else
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel, tmA[0], tmA[1], p));

@@ -9,6 +9,7 @@ struct TcConvPlan {
   alignas(64) uint8_t blob[768];
   int grid;
   int ctas_per_sm;
+  int threads;                    // 320, 192 (three CTAs per SM) or 576 (WIDE)
   size_t smem;
 };
 
@@ -16,6 +17,9 @@ bool tc_halo_enabled();           // KFN_TC_HALO=0 disables the halo-tile varian
 bool tc_prefetch_enabled();       // KFN_TC_PREFETCH=1 enables the producer TMA L2 prefetch (measured: no gain, off by default)
 bool tc_two_ctas_enabled();       // KFN_TC_TWO_CTAS=0: always one CTA per SM (A/B measurements)
 bool tc_three_ctas_enabled();     // KFN_TC_THREE_CTAS=0: at most two CTAs per SM (A/B measurements)
+bool tc_wide_enabled();           // KFN_TC_WIDE: 576-thread four-group epilogue variant for short-tile one-CTA layers
+bool tc_im2col_fused_enabled();   // KFN_TC_IM2COL_FUSED: BF16 first layers build their im2col rows from the u8 image in-kernel
+bool tc_group2_enabled();         // KFN_TC_GROUP2: two-CTA plans alternate tiles between epilogue halves instead of splitting columns
 bool tc_pdl_enabled();            // KFN_TC_PDL=0: plain stream-ordered launches (A/B measurements)
 int tc_pick_kc(int Cin);          // channels per k-block: 64 / 32 / 16 (128B / 64B / 32B swizzle)
 int tc_cout_padded(int Cout);     // weights are packed [tap][CoutP][Cin] bf16 with CoutP = roundup(Cout, 16)

@@ -239,8 +239,11 @@ int pack_first_both(kfn_handle* h) {
 
 // Runs packed op `key`: in (NHWC, `in.C` channel stride, op.Cin channels read from channel 0 of `in.p`)
 // -> out channels [out_coff, out_coff + Cout) of `out` at pixel (my*omul + oaddy, mx*omul + oaddx).
+// `u8_image`: `in.p` is the u8 image [N,H,W,3] and the op is one of the im2col-packed first layers (BF16 mode): the
+// 32-wide operand row is built inside the kernel (conv_tc.cu, fused first layer)
 int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff, int MH, int MW, int omul, int oaddy,
-           int oaddx, int epi, bool out_fp32, cudaStream_t st, void* out2 = nullptr, int split_col = 0, int out2_cs = 0) {
+           int oaddx, int epi, bool out_fp32, cudaStream_t st, void* out2 = nullptr, int split_col = 0, int out2_cs = 0,
+           bool u8_image = false) {
   auto it = h->ops.find(key);
   if (it == h->ops.end()) { set_error("unknown op " + key); return KFN_ERR_STATE; }
   const PackedOp& op = it->second;
@@ -259,6 +262,11 @@ int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
   g.omul = omul; g.oaddy = oaddy; g.oaddx = oaddx; g.relu = op.relu; g.epi = epi;
   g.phase_cout = op.phase_cout;
   g.split_col = split_col; g.out2_cs = out2_cs;
+  g.im2col_u8 = u8_image ? 1 : 0;
+  if (u8_image && (h->mode != KFN_MODE_BF16 || op.Cin != 32 || op.ntaps != 1)) {
+    set_error(key + ": u8 image input is only valid for the BF16-mode first layers");
+    return KFN_ERR_ARG;
+  }
   if (h->mode == KFN_MODE_FP32) {
     return launch_conv_simt(g, reinterpret_cast<const float*>(in.p), reinterpret_cast<const float*>(op.w), op.CoutP,
                             op.bias, reinterpret_cast<float*>(out.p), st);
@@ -288,6 +296,9 @@ int deconv(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
 Act act(void* p, int N, int H, int W, int C, int limbs = 0) { return Act{p, N, H, W, C, limbs}; }
 void* offs(void* p, int64_t elems, int es) { return p ? reinterpret_cast<uint8_t*>(p) + elems * es : nullptr; }
 
+// BF16 mode: first layers read the u8 image directly (KFN_TC_IM2COL_FUSED; otherwise im2col kernel + TMA path)
+bool first_fused(const kfn_handle* h) { return tc_im2col_fused_enabled() && h->mode == KFN_MODE_BF16; }
+
 // ---------------------------------------------------------------------------------------------
 // `shared_pre`: optional already-preprocessed input (im2col / fp32) shared with the feature tower by kfn_eval_sequences
 // `feat1_out`: when given (BF16 mode, kfn_eval_sequences) conv1a also produces the tower's feat1 into this buffer
@@ -295,7 +306,8 @@ int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, 
                    void* shared_pre = nullptr, void* feat1_out = nullptr) {
   const int H = h->H, W = h->W, es = esize(h);
   const int64_t px = (int64_t)B * H * W;
-  void* pre = shared_pre ? shared_pre : ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
+  const bool fused = first_fused(h);
+  void* pre = (shared_pre || fused) ? shared_pre : ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
   void* bufA = ar.alloc(px * 64 * es);
   void* bufB = ar.alloc(px * 64 * es);
   if (dry) return KFN_OK;
@@ -304,6 +316,11 @@ int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, 
   if (h->mode == KFN_MODE_FP32) {
     if (!shared_pre && (rc = launch_preprocess_f32(images, (float*)pre, px * 3, st))) return rc;
     if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 3), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
+  } else if (fused) {
+    Act img = act(const_cast<uint8_t*>(images), B, H, W, 32, 1);
+    if (feat1_out) rc = run_op(h, "first#both", img, act(bufA, B, H, W, 64), 0, H, W, 1, 0, 0, EPI_NONE, false, st, feat1_out, 64, 16, true);
+    else rc = run_op(h, "ScoreNet/conv1a", img, act(bufA, B, H, W, 64), 0, H, W, 1, 0, 0, EPI_NONE, false, st, nullptr, 0, 0, true);
+    if (rc) return rc;
   } else {
     if (!shared_pre && (rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
     if (feat1_out && h->mode == KFN_MODE_BF16) {
@@ -331,7 +348,8 @@ int tower_impl(kfn_handle* h, const uint8_t* images, int B, float* feat, Arena& 
                void* shared_pre = nullptr, void* feat1_done = nullptr) {
   const int H = h->H, W = h->W, es = esize(h);
   const int64_t px = (int64_t)B * H * W;
-  void* pre = shared_pre ? shared_pre : ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
+  const bool fused = first_fused(h);
+  void* pre = (shared_pre || fused) ? shared_pre : ar.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
   void* bufA = feat1_done ? feat1_done : ar.alloc(px * 16 * es);
   void* bufB = ar.alloc(px * 16 * es);
   if (dry) return KFN_OK;
@@ -340,6 +358,10 @@ int tower_impl(kfn_handle* h, const uint8_t* images, int B, float* feat, Arena& 
   if (h->mode == KFN_MODE_FP32) {
     if (!shared_pre && (rc = launch_preprocess_f32(images, (float*)pre, px * 3, st))) return rc;
     if ((rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 3), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
+  } else if (fused) {
+    if (!feat1_done && (rc = run_op(h, "Temporal/feat1", act(const_cast<uint8_t*>(images), B, H, W, 32, 1), act(bufA, B, H, W, 16), 0,
+                                    H, W, 1, 0, 0, EPI_NONE, false, st, nullptr, 0, 0, true)))
+      return rc;
   } else {
     if (!shared_pre && (rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
     if (!feat1_done && (rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
@@ -633,10 +655,11 @@ int eval_sequences_impl(kfn_handle* h, const uint8_t* images, int S, int T, cons
     // both networks start from the same preprocessed input (im2col rows / fp32 image): build it once per batch
     Arena a(sub, sub_bytes);
     const int64_t px = (int64_t)B * h->H * h->W;
-    void* pre = a.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
+    const bool fused = first_fused(h);   // first layers read the u8 frames directly: no preprocessed copy at all
+    void* pre = fused ? nullptr : a.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
     if (a.overflow) { set_error("workspace too small for eval_sequences"); return KFN_ERR_WORKSPACE; }
     if (h->mode == KFN_MODE_FP32) { if ((rc = launch_preprocess_f32(images + f0 * img_bytes, (float*)pre, px * 3, st))) return rc; }
-    else { if ((rc = launch_im2col27_bf16(images + f0 * img_bytes, (__nv_bfloat16*)pre, B, h->H, h->W, st))) return rc; }
+    else if (!fused) { if ((rc = launch_im2col27_bf16(images + f0 * img_bytes, (__nv_bfloat16*)pre, B, h->H, h->W, st))) return rc; }
     static const bool fuse_first = [] { const char* e = getenv("KFN_FUSE_FIRST"); return !(e && e[0] == '0'); }();   // A/B switch
     void* f1 = (h->mode == KFN_MODE_BF16 && fuse_first) ? a.alloc(px * 16 * 2) : nullptr;   // feat1 output, produced by the fused first layer
     if (a.overflow) { set_error("workspace too small for eval_sequences"); return KFN_ERR_WORKSPACE; }
@@ -711,7 +734,13 @@ int kfn_conv_layer(kfn_handle* h, const char* op_key, const void* in, int N, int
                    int OW, int out_cs, int out_coff, int out_fp32, int epi, void* stream) {
   KFN_READY(h);
   KFN_REQUIRE(op_key && in && out && N > 0, "null/empty argument");
-  const std::string key(op_key);
+  std::string key(op_key);
+  if (key.size() > 3 && key.compare(key.size() - 3, 3, "#u8") == 0) {   // first layer straight from the u8 image [N,IH,IW,3]
+    key.resize(key.size() - 3);
+    KFN_REQUIRE(in_cs == 3 && OH == IH && OW == IW, "u8 first layer: in is the [N,IH,IW,3] image, same-size output");
+    return run_op(h, key, act(const_cast<void*>(in), N, IH, IW, 32, 1), act(out, N, OH, OW, out_cs), out_coff, OH, OW, 1, 0, 0, epi,
+                  out_fp32 != 0, (cudaStream_t)stream, nullptr, 0, 0, true);
+  }
   Act a = act(const_cast<void*>(in), N, IH, IW, in_cs);
   Act o = act(out, N, OH, OW, out_cs);
   if (key.size() > 4 && key.compare(key.size() - 4, 4, "#all") == 0) {   // merged conv2d_transpose (all four phases)

@@ -162,7 +162,10 @@ class Engine:
     # ---- one packed layer by name (per-layer tests / roofline) ----
     def conv_layer(self, key, x, out_hw, out_channels, out_coff=0, out=None, out_fp32=False, epi=0):
         N, IH, IW, ics = x.shape
-        assert x.is_contiguous() and x.dtype == (torch.float32 if self.mode == "fp32" else torch.bfloat16)
+        if key.endswith("#u8"):      # BF16-mode first layer straight from the u8 image (fused im2col producer)
+            assert x.is_contiguous() and x.dtype == torch.uint8 and ics == 3
+        else:
+            assert x.is_contiguous() and x.dtype == (torch.float32 if self.mode == "fp32" else torch.bfloat16)
         odt = torch.float32 if (self.mode == "fp32" or out_fp32) else torch.bfloat16
         if out is None:
             out = torch.zeros(N, out_hw[0], out_hw[1], out_channels, dtype=odt, device=x.device)

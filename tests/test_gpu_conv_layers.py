@@ -9,7 +9,7 @@ import torch
 
 from oracle import kfnet_oracle as O
 from tests.golden import cases
-from tests.util import assert_close_rms, gpu_setup
+from tests.util import assert_close_rms, feature_on, gpu_setup
 
 pytestmark = pytest.mark.gpu
 
@@ -118,3 +118,57 @@ def test_first_layer_im2col_weights(engines, weights):
         ref = O.conv2d_same(O.preprocess(img), w, torch.tensor(weights[key + "/bias"]).cuda(), 1, True)
         got = engines["bf16"].conv_layer(key, cols, (16, 24), cout, out_fp32=True)
         assert_close_rms(got, ref, 5e-4, key)
+
+
+@pytest.mark.skipif(not feature_on("KFN_TC_IM2COL_FUSED"), reason="fused u8 first layer not enabled")
+@pytest.mark.parametrize("shape", [(2, 16, 24), (1, 480, 640), (3, 40, 136)])
+def test_first_layer_fused_from_u8(engines, weights, shape):
+    """BF16 mode, default path: the first layers read the u8 image; the 32-wide im2col row (u8 - 128, zero outside the
+    image) is built in shared memory by the kernel's producer warps (no im2col tensor in HBM).  Full-size frames take
+    the 576+96-thread WIDE layout, small ones the 320+96-thread one; N=3 with 8x8x2-pixel tiles has a ragged batch tile."""
+    n, hh, ww = shape
+    g = torch.Generator().manual_seed(5 + hh)
+    img_u8 = torch.randint(0, 256, (n, hh, ww, 3), generator=g, dtype=torch.uint8).cuda()
+    img = img_u8.float()
+    cols = torch.nn.functional.unfold((img - 128.0).permute(0, 3, 1, 2), 3, padding=1).reshape(n, 3, 9, hh, ww)
+    cols = cols.permute(0, 3, 4, 2, 1).reshape(n, hh, ww, 27)
+    cols = torch.cat([cols, torch.zeros(n, hh, ww, 5, device="cuda")], -1).to(torch.bfloat16).contiguous()
+    for key, cout in (("ScoreNet/conv1a", 64), ("Temporal/feat1", 16)):
+        w = (torch.tensor(weights[key + "/kernel"]).cuda() * 0.00625).to(torch.bfloat16).float() / 0.00625
+        ref = O.conv2d_same(O.preprocess(img), w, torch.tensor(weights[key + "/bias"]).cuda(), 1, True)
+        got = engines["bf16"].conv_layer(key + "#u8", img_u8, (hh, ww), cout, out_fp32=True)
+        assert_close_rms(got, ref, 5e-4, key + "#u8 fp32 out")
+        # same operands, same two MMAs per tile as the im2col-tensor + TMA path: bit-identical
+        assert torch.equal(got, engines["bf16"].conv_layer(key, cols, (hh, ww), cout, out_fp32=True)), key + " fused vs TMA path"
+
+        got16 = engines["bf16"].conv_layer(key + "#u8", img_u8, (hh, ww), cout)          # bf16 output: coalesced store path
+        assert_close_rms(got16.float(), ref, 1e-2, key + "#u8 bf16 out")
+        # writes stay inside [out_coff, out_coff + cout) of a wider tensor
+        wide = torch.full((n, hh, ww, cout + 32), 7.0, dtype=torch.bfloat16, device="cuda")
+        engines["bf16"].conv_layer(key + "#u8", img_u8, (hh, ww), cout, out_coff=16, out=wide)
+        assert bool((wide[..., :16] == 7.0).all()) and bool((wide[..., 16 + cout:] == 7.0).all())
+        assert_close_rms(wide[..., 16:16 + cout].float(), ref, 1e-2, key + "#u8 offset")
+
+
+def test_first_layer_fused_rejected_outside_bf16(engines):
+    img = torch.zeros(1, 16, 24, 3, dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError):
+        engines["bf16"].conv_layer("ScoreNet/conv1b#u8", img, (16, 24), 64)
+
+
+@pytest.mark.skipif(not feature_on("KFN_TC_WIDE"), reason="WIDE kernel variant not enabled")
+@pytest.mark.parametrize("shape", [(1, 480, 640), (3, 240, 320)])
+def test_wide_layout_conv1b_full_frame(engines, weights, shape):
+    """conv1b at frame scale takes the WIDE kernel variant (576 threads: four accumulator stages, four epilogue groups
+    draining whole tiles round-robin) on top of the halo-tile MMA path; the small LAYERS shapes stay below its size
+    threshold, so it is checked here against the same fp32 reference (fp32 and bf16 outputs, N=3: ragged last tiles)."""
+    n, hh, ww = shape
+    key = "ScoreNet/conv1b"
+    g = torch.Generator().manual_seed(11 + n)
+    x = torch.randn(n, hh, ww, 64, generator=g).to(torch.bfloat16).cuda().contiguous()
+    ref = _ref_layer(weights, key, "conv", x.float(), 1, True, True)
+    got = engines["bf16"].conv_layer(key, x, (hh, ww), 64, out_fp32=True)
+    assert_close_rms(got, ref, 2e-4, key + " wide fp32 out")
+    got16 = engines["bf16"].conv_layer(key, x, (hh, ww), 64)
+    assert_close_rms(got16.float(), ref, 1e-2, key + " wide bf16 out")
+
