@@ -31,6 +31,8 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
+    extra_env = os.environ.get("KFN_NVCC_EXTRA", "").split()   # e.g. -DKFN_MMA_ELECT=0 for an A/B build (forces a rebuild)
+    force = force or bool(extra_env)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "kfnet_b200.h"))
     objs, procs = [], []
@@ -39,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [_nvcc(), *ARCH, *COMMON, *extra, "-c", s, "-o", o]
+            cmd = [_nvcc(), *ARCH, *COMMON, *extra, *extra_env, "-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -89,6 +89,24 @@ struct __align__(8) TcParams {
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  Unlike `lane == 0`, ptxas knows the guarded region runs in a single thread and emits
+// the uniform-datapath instructions (UTCHMMA, UTMALDG, descriptor arithmetic) directly; behind `lane == 0` it wraps
+// every one of them in an ELECT / BRA.U.ANY loop (~5 extra instructions per MMA: at 36 short MMAs per tile the issuing
+// thread, never waiting, was conv1b's bottleneck -- profiles/r01h).  KFN_MMA_ELECT=0 compiles the old form.
+#ifndef KFN_MMA_ELECT
+#define KFN_MMA_ELECT 1
+#endif
+__device__ __forceinline__ bool elect_one(int lane) {
+#if KFN_MMA_ELECT
+  (void)lane;
+  uint32_t elected;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+  return elected != 0;
+#else
+  return lane == 0;
+#endif
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -430,16 +448,32 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
       float e[32];
 #pragma unroll
       for (int k = 27; k < 32; ++k) e[k] = 0.f;
+      const uint8_t* src0 = p.img + (((int64_t)n * H + (y - 1)) * W + (x - 1)) * 3;   // window row 0, column x-1
+      const bool xl = x > 0, xr = x + 1 < W;
+      if (n < p.N && y > 0 && y + 1 < H) {
+        // interior rows (all but 2 of H; warp-uniform for row-segment tiles): 27 byte loads, only the window's
+        // left / right column predicated -- the fully predicated form below costs ~550 instructions per pixel row and
+        // made these four warps the layer's bottleneck (profiles/r01h)
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yy = y + ky - 1;
-        const bool rowv = n < p.N && yy >= 0 && yy < H;
-        const uint8_t* src = p.img + (((int64_t)n * H + yy) * W + (x - 1)) * 3;
+        for (int ky = 0; ky < 3; ++ky) {
+          const uint8_t* src = src0 + (int64_t)ky * W * 3;
 #pragma unroll
-        for (int jj = 0; jj < 9; ++jj) {
-          const int xx = x - 1 + jj / 3;
-          const bool v = rowv && xx >= 0 && xx < W;
-          e[ky * 9 + jj] = v ? (float)__ldg(src + jj) - 128.0f : 0.f;
+          for (int jj = 0; jj < 9; ++jj) {
+            const bool v = jj < 3 ? xl : (jj >= 6 ? xr : true);
+            e[ky * 9 + jj] = v ? (float)__ldg(src + jj) - 128.0f : 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int yy = y + ky - 1;
+          const bool rowv = n < p.N && yy >= 0 && yy < H;
+          const uint8_t* src = src0 + (int64_t)ky * W * 3;
+#pragma unroll
+          for (int jj = 0; jj < 9; ++jj) {
+            const bool v = rowv && (jj < 3 ? xl : (jj >= 6 ? xr : true));
+            e[ky * 9 + jj] = v ? (float)__ldg(src + jj) - 128.0f : 0.f;
+          }
         }
       }
       uint4 c[4];
@@ -458,7 +492,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
     }
   } else if (warp == 0) {
     // ===================================================================== TMA producer (one lane)
-    if (lane == 0 && p.halo) {
+    const bool producer_lane = elect_one(lane);
+    if (producer_lane && p.halo) {
       // resident weights: every (tap, chunk) tile once, one barrier
       const uint32_t wbar = smem_u32(&s_wbar);
       mbar_expect_tx(wbar, (uint32_t)(p.ntaps * p.kchunks) * p.b_bytes);
@@ -488,7 +523,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
-    } else if (lane == 0) {
+    } else if (producer_lane) {
       int s = 0;
       uint32_t ph = 0;
       TileIter it, pf;
@@ -529,7 +564,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (one lane)
-    if (lane == 0) {
+    if (elect_one(lane)) {
       const int ksteps = p.KC >> 4;
       if (f_im2col) {
         mma_role_im2col<2>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
@@ -835,21 +870,21 @@ bool tc_three_ctas_enabled() {
   static const bool on = [] { const char* e = getenv("KFN_TC_THREE_CTAS"); return !(e && e[0] == '0'); }();
   return on;
 }
-// variants awaiting their B200 validation run are opt-in (=1); validated ones are on unless =0
+// kernel-variant switches for A/B measurements: NAME=0 disables, NAME=1 enables, unset = default
 bool env_flag(const char* name, bool dflt) {
   const char* e = getenv(name);
   return (e && e[0]) ? e[0] != '0' : dflt;
 }
 bool tc_wide_enabled() {
-  static const bool on = env_flag("KFN_TC_WIDE", false);
+  static const bool on = env_flag("KFN_TC_WIDE", true);
   return on;
 }
 bool tc_group2_enabled() {
-  static const bool on = env_flag("KFN_TC_GROUP2", false);
+  static const bool on = env_flag("KFN_TC_GROUP2", true);
   return on;
 }
 bool tc_im2col_fused_enabled() {
-  static const bool on = env_flag("KFN_TC_IM2COL_FUSED", false);
+  static const bool on = env_flag("KFN_TC_IM2COL_FUSED", true);
   return on;
 }
 bool tc_pdl_enabled() {
