@@ -170,9 +170,11 @@ KFN_API int kfn_eval_sequences_host(kfn_handle* h, const uint8_t* host_images, i
 
 /* One packed layer of the path by name (per-layer parity tests and per-layer roofline measurements).
  *   op_key: "<scope>/<layer>" for conv / dense layers, "<scope>/<layer>#p<k>" (k = 2*py+px) for one sub-pixel phase
- *           of a conv2d_transpose, "<scope>/<layer>#all" for all four phases in one GEMM (cnn_wrapper/network.py:116-135, :418-437).
+ *           of a conv2d_transpose, "<scope>/<layer>#all" for all four phases in one GEMM (cnn_wrapper/network.py:116-135, :418-437),
+ *           "ScoreNet/conv1a#u8" / "Temporal/feat1#u8" (KFN_MODE_BF16) for the first layers fed with the u8 image itself.
  *   in    : device NHWC [N,IH,IW,in_cs] -- fp32 in KFN_MODE_FP32, bf16 in KFN_MODE_BF16 (the first Cin channels are read;
- *           for the Cin=3 first layers in BF16 mode `in` is the 32-wide im2col buffer)
+ *           for the Cin=3 first layers in BF16 mode `in` is the 32-wide im2col buffer of u8-128 values, or with "#u8" the
+ *           uint8 image [N,IH,IW,3] (in_cs = 3): the kernel builds the same rows in shared memory -- the path the networks use)
  *   out   : device NHWC [N,OH,OW,out_cs], channels [out_coff, out_coff+Cout) written; bf16 unless out_fp32 (FP32 mode: always fp32)
  *   epi   : 0 none, 1 exp on channel 3 (SCoordNet.py:43), 2 l2-normalise 32 channels (KFNet.py:340; BF16 mode only) */
 KFN_API int kfn_conv_layer(kfn_handle* h, const char* op_key, const void* in, int N, int IH, int IW, int in_cs, void* out,
