@@ -3,6 +3,7 @@
 // See include/kfnet_b200.h for the contract and the reference functions each entry point replaces.
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <map>
 #include <string>
 #include <tuple>
@@ -85,7 +86,10 @@ struct kfn_handle {
   std::map<std::string, std::vector<float>> host_w;
   std::map<std::string, PackedOp> ops;
   std::vector<void*> allocs;
-  std::map<std::tuple<std::string, const void*, void*, int>, TcConvPlan> plans;
+  // launch plans (tensor maps + kernel parameters) keyed by op, buffers AND the full geometry: kfn_conv_layer may be
+  // called with different shapes / channel offsets / output types on recycled device pointers
+  typedef std::tuple<std::string, const void*, void*, void*, std::array<int, 18>> PlanKey;
+  std::map<PlanKey, TcConvPlan> plans;
   bool finalized = false;
   // kfn_eval_sequences_host: internal copy stream and per-batch events (library-owned)
   cudaStream_t copy_stream = nullptr;
@@ -271,7 +275,9 @@ int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
     return launch_conv_simt(g, reinterpret_cast<const float*>(in.p), reinterpret_cast<const float*>(op.w), op.CoutP,
                             op.bias, reinterpret_cast<float*>(out.p), st);
   }
-  auto pk = std::make_tuple(key, (const void*)in.p, out.p, in.N);
+  const kfn_handle::PlanKey pk(key, (const void*)in.p, out.p, out2,
+                               std::array<int, 18>{in.N, in.H, in.W, g.in_cs, MH, MW, out.H, out.W, g.out_cs, out_coff, omul, oaddy,
+                                                   oaddx, epi, out_fp32 ? 1 : 0, split_col, out2_cs, g.im2col_u8});
   auto pit = h->plans.find(pk);
   if (pit == h->plans.end()) {
     TcConvPlan plan;
