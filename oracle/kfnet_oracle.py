@@ -377,3 +377,34 @@ def dist_error(coords, gt_coords, mask):
     v = d.reshape(-1)
     v = v[v > 0]
     return (float(np.median(v)) * 100.0 if v.size else float("nan")), d * 100.0
+
+
+def coord_loss_with_uncertainty(pred, unc, gt_full, mask_full, transform, dist_threshold=0.05, min_uncertainty=1e-5):
+    """KFNet.CoordLossWithUncertainty as KF_fusion calls it (KFNet.py:192-232, train.py:254-259): `transform` applied
+    to the prediction, full-resolution labels nearest-neighbour downsampled to the prediction grid (TF-1.13
+    resize_nearest_neighbor: src = floor(dst * in / out)), mask kept where == 1.0 (`mask_full=None`: no mask, then
+    valid_pixel = B*H*W without the +1).  Note the reference's `tf.minimum(loss_map, -2.0)` (sic, KFNet.py:217)."""
+    pred = np.asarray(pred, np.float64); unc = np.asarray(unc, np.float64)
+    T = np.asarray(transform, np.float64)
+    pred = pred @ T[:3, :3].T + T[:3, 3]
+    b, h, w, _ = pred.shape
+    def down(a):
+        a = np.asarray(a, np.float64)
+        ys = np.minimum(np.floor(np.arange(h) * (a.shape[1] / h)).astype(int), a.shape[1] - 1)
+        xs = np.minimum(np.floor(np.arange(w) * (a.shape[2] / w)).astype(int), a.shape[2] - 1)
+        return a[:, ys][:, :, xs]
+    gt = down(gt_full)
+    d = np.square(pred - gt).sum(-1, keepdims=True)
+    u = np.maximum(unc, min_uncertainty)
+    loss_map = np.minimum(3.0 * np.log(u) + d / (2.0 * np.square(u)), -2.0)
+    if mask_full is not None:
+        mask = (down(mask_full) == 1.0).astype(np.float64)
+        valid = mask.sum() + 1.0
+        d = d * mask
+        loss_map = loss_map * mask
+    else:
+        valid = float(b * h * w)
+    loss = loss_map.sum() / valid
+    acc = (valid - np.count_nonzero(np.maximum(d - dist_threshold * dist_threshold, 0))) / valid
+    return float(loss), float(acc)
+

@@ -6,7 +6,7 @@ tools/util.py) are py3-parseable.  Putting this package first on sys.path lets
 tests/golden/make_golden.py IMPORT AND EXECUTE those files unmodified (eager instead of graph
 mode), so the golden vectors under tests/golden/ pin the oracle's graph wiring (layer order,
 slicing, concat order, offsets table, sampler index arithmetic, Kalman algebra) to the reference
-source.  Only the ~50 tf.* symbols the eval path touches exist; each follows the TF-1.13 op
+source.  Only the ~55 tf.* symbols the eval path (incl. the printed loss / accuracy) touches exist; each follows the TF-1.13 op
 definition.  Nothing under kfnet_b200/ imports this.
 """
 import builtins as _b
@@ -115,6 +115,36 @@ def equal(a, b): return _t(a) == b
 
 def maximum(a, b, name=None):
     return torch.maximum(_t(a), torch.as_tensor(b, dtype=_t(a).dtype))
+
+
+def minimum(a, b, name=None):
+    return torch.minimum(_t(a), torch.as_tensor(b, dtype=_t(a).dtype))
+
+
+def log(x, name=None): return torch.log(x)
+
+
+def reduce_sum(x, axis=None, keepdims=False, name=None):
+    x = _t(x)
+    return x.sum() if axis is None else x.sum(dim=axis, keepdim=keepdims)
+
+
+def count_nonzero(x, name=None):
+    return (_t(x) != 0).sum()
+
+
+def _resize_nearest_neighbor(images, size, align_corners=False):
+    """tf.image.resize_nearest_neighbor, TF-1.13 default (align_corners=False, no half-pixel centres):
+    src = min(floor(dst * in / out), in - 1)."""
+    assert not align_corners
+    n, h, w, c = images.shape
+    oh, ow = int(size[0]), int(size[1])
+    ys = torch.clamp(torch.floor(torch.arange(oh, dtype=torch.float64) * (h / oh)).long(), max=h - 1)
+    xs = torch.clamp(torch.floor(torch.arange(ow, dtype=torch.float64) * (w / ow)).long(), max=w - 1)
+    return images[:, ys][:, :, xs]
+
+
+image = types.SimpleNamespace(resize_nearest_neighbor=_resize_nearest_neighbor)
 
 
 def clip_by_value(x, lo, hi):

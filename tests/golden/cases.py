@@ -65,3 +65,26 @@ def full_state():
 
 def transform():
     return np.linalg.inv(synth.make_transform(2)).astype(np.float64)
+
+
+
+def label_case(n=1, seed=31):
+    """Full-resolution labels for the printed metrics (train.py:219-222, KFNet.py:192-232, eval.py:10-29):
+    gt coords [n,H,W,3], mask [n,H,W,1] with 1.0 / 0.0 and a few other values (the reference keeps only mask == 1.0
+    after the nearest-neighbour downsample), predictions near the ground truth so both sides of the 5 cm accuracy
+    threshold and of the loss clamp occur, sigma spanning the min_uncertainty clamp."""
+    rng = np.random.default_rng(seed)
+    H, W = SMALL_HW
+    gt = rng.normal(size=(n, H, W, 3))
+    mask = (rng.uniform(size=(n, H, W, 1)) > 0.3).astype(np.float64)
+    mask[:, ::5, ::7] = 0.5                                       # neither 0 nor 1
+    h, w = H // 8, W // 8
+    gt8 = gt[:, ::8, ::8]
+    scale = np.where(rng.uniform(size=(n, h, w, 1)) > 0.5, 0.01, 0.2)
+    pred_world = gt8 + rng.normal(size=(n, h, w, 3)) * scale     # what T . pred must equal
+    T = transform()
+    pred = (pred_world - T[:3, 3]) @ np.linalg.inv(T[:3, :3]).T   # prediction in the network's frame
+    unc = np.exp(rng.uniform(np.log(3e-6), np.log(0.5), size=(n, h, w, 1)))
+    nis = np.exp(rng.normal(size=(1, h, w, 3)) * 2.0 - 1.0) * (rng.uniform(size=(1, h, w, 3)) > 0.1)
+    return dict(gt=gt, mask=mask, pred=pred, unc=unc, nis=nis)
+

@@ -80,6 +80,32 @@ def main():
     path = os.path.join(HERE, "kfnet_reference_on_shim.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()})
+    metrics(net)
+
+
+def metrics(net):
+    """6. the printed eval metrics: KFNet.CoordLossWithUncertainty exactly as KF_fusion calls it (train.py:254-259:
+    full-resolution labels, downsample=True, transform) and eval.py's dist_error / get_NIS_measurement.  eval.py is
+    python-2 source (print statements), so the two function definitions are cut out of its text and exec'ed with a
+    list-returning `filter` -- the reference's own lines, not a restatement."""
+    lc = cases.label_case()
+    T = tf.constant(cases.transform())
+    out = {}
+    for tag, mask in (("masked", tf.constant(lc["mask"])), ("nomask", None)):
+        loss, acc = net.CoordLossWithUncertainty(tf.constant(lc["pred"]), tf.constant(lc["unc"]), tf.constant(lc["gt"]),
+                                                 mask=mask, transform=T, downsample=True)
+        out["loss_" + tag] = np.asarray(float(loss)); out["accuracy_" + tag] = np.asarray(float(acc))
+    src = open(os.path.join(REF, "KFNet", "eval.py")).read()
+    chunk = src[src.index("def get_NIS_measurement"):src.index("def eval(")]
+    ns = {"np": np, "filter": lambda f, xs: list(builtins.filter(f, xs))}
+    exec(compile(chunk, os.path.join(REF, "KFNet", "eval.py"), "exec"), ns)
+    out["nis_fraction"] = np.asarray(ns["get_NIS_measurement"](lc["nis"]))
+    world = npy(ref_util.ApplyTransform(tf.constant(lc["pred"]), T))[0]
+    med, dmap = ns["dist_error"](world, lc["gt"][0, ::8, ::8], lc["mask"][0, ::8, ::8])
+    out["dist_median_cm"] = np.asarray(med); out["dist_map_cm"] = dmap
+    path = os.path.join(HERE, "kfnet_reference_metrics_on_shim.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: (v.shape, float(v) if v.ndim == 0 else None) for k, v in out.items()})
 
 
 if __name__ == "__main__":

@@ -74,3 +74,32 @@ def test_eval_sequence_matches_recursive_steps(weights):
     for i in range(4):
         np.testing.assert_allclose(kc[i].numpy(), b[i].kf_coord[0].numpy(), rtol=1e-9, atol=1e-11)
         np.testing.assert_allclose(ku[i].numpy(), b[i].kf_unc[0].numpy(), rtol=1e-9, atol=1e-11)
+
+
+def test_printed_metrics_match_reference_code():
+    """Loss / accuracy (KFNet.CoordLossWithUncertainty as KF_fusion calls it), NIS in-band fraction and median distance
+    error (eval.py:10-29): the oracle restatement AND the product's host functions against values produced by the
+    reference's own source (tests/golden/make_golden.py::metrics)."""
+    import os
+    from kfnet_b200 import eval as P
+    g = np.load(os.path.join(os.path.dirname(cases.__file__), "kfnet_reference_metrics_on_shim.npz"))
+    lc = cases.label_case()
+    T = cases.transform()
+    loss, acc = O.coord_loss_with_uncertainty(lc["pred"], lc["unc"], lc["gt"], lc["mask"], T)
+    assert abs(loss - float(g["loss_masked"])) <= 1e-12 * abs(float(g["loss_masked"])) and acc == float(g["accuracy_masked"])
+    loss, acc = O.coord_loss_with_uncertainty(lc["pred"], lc["unc"], lc["gt"], None, T)
+    assert abs(loss - float(g["loss_nomask"])) <= 1e-12 * abs(float(g["loss_nomask"])) and acc == float(g["accuracy_nomask"])
+    assert O.nis_in_band_fraction(lc["nis"]) == float(g["nis_fraction"])
+    world = lc["pred"][0] @ T[:3, :3].T + T[:3, 3]
+    gt8, mask8 = lc["gt"][0, ::8, ::8], lc["mask"][0, ::8, ::8]
+    med, dmap = O.dist_error(world, gt8, mask8)
+    assert abs(med - float(g["dist_median_cm"])) <= 1e-12 and np.allclose(dmap, g["dist_map_cm"], rtol=1e-12, atol=0)
+    # product host functions (kfnet_b200/eval.py; fp32 label-grid inputs as eval() feeds them)
+    loss_p, acc_p = P.coord_loss_with_uncertainty(lc["pred"][0].astype(np.float32), lc["unc"][0].astype(np.float32),
+                                                  gt8.astype(np.float32), mask8.astype(np.float32), T.astype(np.float32))
+    assert abs(loss_p - float(g["loss_masked"])) <= 2e-5 * abs(float(g["loss_masked"]))
+    assert abs(acc_p - float(g["accuracy_masked"])) <= 1.5 / 96                     # one borderline pixel of 96 at fp32
+    assert P.get_NIS_measurement(lc["nis"]) == float(g["nis_fraction"])
+    med_p, dmap_p = P.dist_error(world.astype(np.float32), gt8.astype(np.float32), mask8.astype(np.float32))
+    assert abs(med_p - float(g["dist_median_cm"])) <= 1e-4 and np.allclose(dmap_p, g["dist_map_cm"], rtol=1e-4, atol=1e-5)
+
