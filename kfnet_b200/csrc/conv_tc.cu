@@ -823,6 +823,11 @@ __global__ void __launch_bounds__(kThreads, 2)
 conv_tc_kernel_x2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   conv_tc_body<false, false>(tmA, tmB, p);
 }
+// co-resident CTAs for plain bf16 layers (most of the U-Net and the tower): the lean body
+__global__ void __launch_bounds__(kThreads, 2)
+conv_tc_kernel_x2_lean(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  conv_tc_body<true, false>(tmA, tmB, p);
+}
 // WIDE: 16 epilogue warps (four groups draining four tiles concurrently) for one-CTA layers with short tiles.
 __global__ void __launch_bounds__(kThreadsWide, 1)
 conv_tc_kernel_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -881,6 +886,10 @@ bool tc_wide_enabled() {
 }
 bool tc_group2_enabled() {
   static const bool on = env_flag("KFN_TC_GROUP2", true);
+  return on;
+}
+bool tc_lean_x2_enabled() {
+  static const bool on = env_flag("KFN_TC_LEAN_X2", true);
   return on;
 }
 bool tc_im2col_fused_enabled() {
@@ -1014,6 +1023,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
                     (int64_t)g.N * g.MH * g.MW >= (int64_t)kBlockM * 8 * num_sms;
   p.lg_groups = -1; p.lg_acc = 1;
   plan->threads = plan->ctas_per_sm == 3 ? 192 : kThreads;
+  plan->lean = (lean_ok && tc_lean_x2_enabled()) ? 1 : 0;
   if (wide) {
     p.lg_groups = 2; p.lg_acc = 2; p.epi_warps = 16;
     p.acc_stride = (uint32_t)(BN + 31) & ~31u;
@@ -1116,6 +1126,7 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
     const int max_smem = 201 * 1024 + 1024 + (int)kEpiStageBytes;
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, 106 * 1024));
+    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_x2_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, 106 * 1024));
     // WIDE: 184 KB pipeline + 32 KB staging + 1 KB alignment; first layer in the 320-thread layout: 200 + 16 + 1 KB
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_first, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
@@ -1138,6 +1149,8 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_first, tmA[0], tmA[1], p));
   else if (plan.threads == kThreadsWide)
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_wide, tmA[0], tmA[1], p));
+  else if (plan.ctas_per_sm >= 2 && plan.lean)
+    KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_x2_lean, tmA[0], tmA[1], p));
   else if (plan.ctas_per_sm >= 2)
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_x2, tmA[0], tmA[1], p));
   else
