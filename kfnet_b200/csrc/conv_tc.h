@@ -31,4 +31,18 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
                     void* out, int out_bf16, int num_sms, TcConvPlan* plan, void* out2 = nullptr);
 int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st);
 
+// conv1a (+ tower feat1) and conv1b of SCoordNet as one kernel (conv1ab_fused.cu; KFN_TC_FUSE_CONV1=1, not yet validated
+// on hardware).  img: u8 [N,H,W,3]; w1_packed: bf16 [80][32] ("first#both"), bias1 [80]; w2_packed: bf16 [9][64][64]
+// ("ScoreNet/conv1b"), bias2 [64]; out: bf16 [N,H,W,64] = conv1b's output; feat1: bf16 [N,H,W,16] or null.
+struct Conv1abPlan {
+  alignas(64) uint8_t blob[768];
+  int grid;
+  size_t smem;
+};
+bool tc_fuse_conv1_enabled();
+bool conv1ab_shape_ok(int H, int W);
+int prepare_conv1ab(const uint8_t* img, int N, int H, int W, const void* w1_packed, const float* bias1, const void* w2_packed,
+                    const float* bias2, void* out, void* feat1, int num_sms, Conv1abPlan* plan);
+int launch_conv1ab(const Conv1abPlan& plan, cudaStream_t st);
+
 }  // namespace kfn

@@ -90,6 +90,7 @@ struct kfn_handle {
   // called with different shapes / channel offsets / output types on recycled device pointers
   typedef std::tuple<std::string, const void*, void*, void*, std::array<int, 18>> PlanKey;
   std::map<PlanKey, TcConvPlan> plans;
+  std::map<std::tuple<const void*, void*, void*, int, int, int>, Conv1abPlan> fused_plans;   // (img, out, feat1, N, H, W)
   bool finalized = false;
   // kfn_eval_sequences_host: internal copy stream and per-batch events (library-owned)
   cudaStream_t copy_stream = nullptr;
@@ -305,6 +306,26 @@ void* offs(void* p, int64_t elems, int es) { return p ? reinterpret_cast<uint8_t
 // BF16 mode: first layers read the u8 image directly (KFN_TC_IM2COL_FUSED; otherwise im2col kernel + TMA path)
 bool first_fused(const kfn_handle* h) { return tc_im2col_fused_enabled() && h->mode == KFN_MODE_BF16; }
 
+// conv1a (+feat1) -> conv1b in one kernel (conv1ab_fused.cu): `out` = conv1b's output [N,H,W,64] bf16, `feat1` optional
+int run_conv1ab(kfn_handle* h, const uint8_t* images, int N, int H, int W, void* out, void* feat1, cudaStream_t st) {
+  auto a = h->ops.find("first#both"), b = h->ops.find("ScoreNet/conv1b");
+  if (h->mode != KFN_MODE_BF16 || a == h->ops.end() || b == h->ops.end() || b->second.ntaps != 9) {
+    set_error("fused conv1a+conv1b: BF16 mode with all nine conv1b taps only");
+    return KFN_ERR_STATE;
+  }
+  auto key = std::make_tuple((const void*)images, out, feat1, N, H, W);
+  auto it = h->fused_plans.find(key);
+  if (it == h->fused_plans.end()) {
+    Conv1abPlan plan;
+    int rc = prepare_conv1ab(images, N, H, W, a->second.w, a->second.bias, b->second.w, b->second.bias, out, feat1, h->num_sms, &plan);
+    if (rc != KFN_OK) return rc;
+    if (h->fused_plans.size() > 1024) h->fused_plans.clear();
+    it = h->fused_plans.emplace(key, plan).first;
+  }
+  return launch_conv1ab(it->second, st);
+}
+bool fuse_conv1(const kfn_handle* h) { return first_fused(h) && tc_fuse_conv1_enabled() && conv1ab_shape_ok(h->H, h->W); }
+
 // ---------------------------------------------------------------------------------------------
 // `shared_pre`: optional already-preprocessed input (im2col / fp32) shared with the feature tower by kfn_eval_sequences
 // `feat1_out`: when given (BF16 mode, kfn_eval_sequences) conv1a also produces the tower's feat1 into this buffer
@@ -322,6 +343,8 @@ int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, 
   if (h->mode == KFN_MODE_FP32) {
     if (!shared_pre && (rc = launch_preprocess_f32(images, (float*)pre, px * 3, st))) return rc;
     if ((rc = conv(h, "ScoreNet/conv1a", act(pre, B, H, W, 3), act(bufA, B, H, W, 64), 0, EPI_NONE, false, st))) return rc;
+  } else if (fuse_conv1(h)) {
+    if ((rc = run_conv1ab(h, images, B, H, W, bufB, feat1_out, st))) return rc;   // conv1a never materialised
   } else if (fused) {
     Act img = act(const_cast<uint8_t*>(images), B, H, W, 32, 1);
     if (feat1_out) rc = run_op(h, "first#both", img, act(bufA, B, H, W, 64), 0, H, W, 1, 0, 0, EPI_NONE, false, st, feat1_out, 64, 16, true);
@@ -338,9 +361,11 @@ int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, 
   struct Step { const char* name; int div; int c; };
   const Step steps[] = {{"conv1b", 1, 64},  {"conv2a", 2, 256}, {"conv2b", 2, 256}, {"conv3a", 4, 512}, {"conv3b", 4, 512},
                         {"conv4a", 8, 1024}, {"conv4b", 8, 1024}, {"conv5", 8, 512}, {"conv6", 8, 256}, {"conv7", 8, 128}};
-  Act cur = act(bufA, B, H, W, 64);
-  void* nextbuf = bufB;
+  const bool conv1b_done = h->mode != KFN_MODE_FP32 && fuse_conv1(h);
+  Act cur = act(conv1b_done ? bufB : bufA, B, H, W, 64);
+  void* nextbuf = conv1b_done ? bufA : bufB;
   for (const Step& s : steps) {
+    if (conv1b_done && &s == &steps[0]) continue;
     Act nxt = act(nextbuf, B, H / s.div, W / s.div, s.c);
     if ((rc = conv(h, std::string("ScoreNet/") + s.name, cur, nxt, 0, EPI_NONE, false, st))) return rc;
     nextbuf = cur.p; cur = nxt;
@@ -503,7 +528,7 @@ int kfn_finalize_weights(kfn_handle* h) {
   KFN_REQUIRE(h, "null handle");
   KFN_CUDA_OK(cudaSetDevice(h->device));
   for (void* p : h->allocs) cudaFree(p);
-  h->allocs.clear(); h->ops.clear(); h->plans.clear();
+  h->allocs.clear(); h->ops.clear(); h->plans.clear(); h->fused_plans.clear();
   const bool bf16 = is_tc(h);
   // spatial dims (output m-grid MH x MW, input IH x IW) of every layer, for tap pruning
   int rc;
@@ -741,6 +766,11 @@ int kfn_conv_layer(kfn_handle* h, const char* op_key, const void* in, int N, int
   KFN_READY(h);
   KFN_REQUIRE(op_key && in && out && N > 0, "null/empty argument");
   std::string key(op_key);
+  if (key == "ScoreNet/conv1ab#u8") {   // conv1a -> conv1b fused (conv1ab_fused.cu); out = conv1b's output, bf16 [N,IH,IW,64]
+    KFN_REQUIRE(in_cs == 3 && OH == IH && OW == IW && out_cs == 64 && out_coff == 0 && !out_fp32 && epi == 0 && conv1ab_shape_ok(IH, IW),
+                "fused conv1a+conv1b: u8 [N,IH,IW,3] in, bf16 [N,IH,IW,64] out, IH % 16 == 0, IW % 8 == 0");
+    return run_conv1ab(h, reinterpret_cast<const uint8_t*>(in), N, IH, IW, out, nullptr, (cudaStream_t)stream);
+  }
   if (key.size() > 3 && key.compare(key.size() - 3, 3, "#u8") == 0) {   // first layer straight from the u8 image [N,IH,IW,3]
     key.resize(key.size() - 3);
     KFN_REQUIRE(in_cs == 3 && OH == IH && OW == IW, "u8 first layer: in is the [N,IH,IW,3] image, same-size output");

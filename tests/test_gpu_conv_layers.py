@@ -172,3 +172,21 @@ def test_wide_layout_conv1b_full_frame(engines, weights, shape):
     got16 = engines["bf16"].conv_layer(key, x, (hh, ww), 64)
     assert_close_rms(got16.float(), ref, 1e-2, key + " wide bf16 out")
 
+
+@pytest.mark.skipif(not feature_on("KFN_TC_FUSE_CONV1"), reason="fused conv1a+conv1b kernel is opt-in (KFN_TC_FUSE_CONV1=1) until validated")
+@pytest.mark.parametrize("shape", [(2, 16, 24), (1, 480, 640), (3, 48, 136)])
+def test_fused_conv1ab(engines, weights, shape):
+    """conv1a -> ReLU -> bf16 -> conv1b -> ReLU in one kernel (conv1ab_fused.cu): the 64-channel intermediate never
+    leaves the SM.  Same bf16 intermediate and the same MMA order as the two-kernel path, so the result must be
+    bit-identical to it, and within bf16 output rounding of the fp32 reference built from the same rounded operands."""
+    n, hh, ww = shape
+    g = torch.Generator().manual_seed(17 + hh)
+    img_u8 = torch.randint(0, 256, (n, hh, ww, 3), generator=g, dtype=torch.uint8).cuda()
+    e = engines["bf16"]
+    mid = e.conv_layer("ScoreNet/conv1a#u8", img_u8, (hh, ww), 64)                    # bf16 intermediate, two-kernel path
+    two = e.conv_layer("ScoreNet/conv1b", mid, (hh, ww), 64)
+    fused = e.conv_layer("ScoreNet/conv1ab#u8", img_u8, (hh, ww), 64)
+    assert torch.equal(fused, two), "fused conv1a+conv1b differs from the two-kernel path"
+    ref = _ref_layer(weights, "ScoreNet/conv1b", "conv", mid.float(), 1, True, True)
+    assert_close_rms(fused.float(), ref, 1e-2, "fused conv1ab vs fp32 reference")
+
