@@ -30,6 +30,7 @@ class Engine:
         _lib.check(self.lib.kfn_create(C.byref(h), self.device, MODES[mode], self.H, self.W))
         self.h = h
         self._ws = None
+        self._graphs = {}
         self.load_weights(weights)
 
     # ---- weights (replaces tf.train.Saver restore by variable name, train.py:317-321) ----
@@ -41,6 +42,7 @@ class Engine:
             dims = (C.c_int64 * a.ndim)(*a.shape)
             _lib.check(self.lib.kfn_load_weight(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), dims, a.ndim))
         _lib.check(self.lib.kfn_finalize_weights(self.h))
+        self._graphs = {}          # packed weights were re-allocated: graphs captured before are stale
 
     def close(self):
         if getattr(self, "h", None):
@@ -63,6 +65,7 @@ class Engine:
     def _workspace(self, nbytes: int):
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = None
+            self._graphs = {}      # captured graphs have the old workspace pointer baked in: drop them with it
             self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self._dev())
         return self._ws
 
@@ -112,8 +115,6 @@ class Engine:
                                pairs_per_batch=4):
         key = (images.data_ptr(), out.data_ptr(), tuple(images.shape), int(reinit_period), bool(nis_gate),
                int(frames_per_batch), int(pairs_per_batch), np.asarray(transform, dtype=np.float32).tobytes())
-        if not hasattr(self, "_graphs"):
-            self._graphs = {}
         g = self._graphs.get(key)
         if g is None:
             # warm-up outside capture (workspace allocation, TMA descriptor cache, function attributes)
