@@ -49,6 +49,21 @@ def test_conv_same_matches_naive(h, w, k, s):
     np.testing.assert_allclose(got, naive_conv_same(x, wt, b, s), rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("h,w,k,s", [(6, 8, 3, 1), (6, 8, 3, 2), (7, 9, 3, 2), (8, 12, 1, 1), (5, 5, 3, 1), (64, 96, 3, 2)])
+def test_conv_same_matches_third_party_tf_padding(h, w, k, s):
+    """Independent statement of TensorFlow's SAME padding that ships in this image: Hugging Face's `apply_tf_padding`
+    (written to run TF-trained MobileNet checkpoints in PyTorch, citing tf.nn's padding notes) + a VALID torch conv."""
+    hf = pytest.importorskip("transformers.models.mobilenet_v1.modeling_mobilenet_v1")
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(2, h, w, 3)); wt = rng.normal(size=(k, k, 3, 5)); b = rng.normal(size=5)
+    conv = torch.nn.Conv2d(3, 5, k, stride=s, padding=0, bias=True).double()
+    with torch.no_grad():
+        conv.weight.copy_(torch.tensor(wt).permute(3, 2, 0, 1)); conv.bias.copy_(torch.tensor(b))
+        ref = conv(hf.apply_tf_padding(torch.tensor(x).permute(0, 3, 1, 2), conv)).permute(0, 2, 3, 1).numpy()
+    got = O.conv2d_same(torch.tensor(x), torch.tensor(wt), torch.tensor(b), s, relu=False).numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12)
+
+
 def test_conv_same_stride2_pads_bottom_right_only():
     x = np.zeros((1, 4, 4, 1)); x[0, 0, 0, 0] = 1.0
     w = np.zeros((3, 3, 1, 1)); w[0, 0, 0, 0] = 1.0           # tap (0,0) must sit on input (2i,2j)
