@@ -84,3 +84,22 @@ def test_pair_stream_and_file_io(tmp_path):
     lst = tmp_path / "l.txt"
     lst.write_text("a.png \nb.png\n")
     assert ev.read_lines(str(lst)) == ["a.png", "b.png"]
+
+
+def test_c_consumer(tmp_path):
+    """include/kfnet_b200.h is plain C: a C99 program compiles against it (-Wall -Wextra -Werror), dlopens the library,
+    finds every entry point and gets loud errors (never a fallback) for bad arguments / a missing GPU."""
+    import shutil
+    import subprocess
+    from kfnet_b200 import build
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "kfn_c_smoke")
+    subprocess.run([gcc, "-O1", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c_abi", "smoke.c"), "-o", exe, "-ldl"], check=True)
+    r = subprocess.run([exe, build.build()], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "c-abi smoke: ok" in r.stdout
+
