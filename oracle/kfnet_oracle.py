@@ -64,7 +64,7 @@ def conv2d_same(x, w, b, stride=1, relu=True):
     pw = max((ow - 1) * stride + kw - wd, 0)
     xt = x.permute(0, 3, 1, 2)
     xt = F.pad(xt, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
-    y = F.conv2d(xt, w.permute(3, 2, 0, 1), b, stride=stride)
+    y = F.conv2d(xt, w.permute(3, 2, 0, 1).contiguous(), b, stride=stride)   # contiguous: CPU autograd needs it
     if relu:
         y = torch.relu(y)
     return y.permute(0, 2, 3, 1).contiguous()
@@ -78,7 +78,7 @@ def conv2d_transpose_same(x, w, b, relu=True):
     kh, kw, cout, cin = w.shape
     n, h, wd, c = x.shape
     assert c == cin and kh == 3 and kw == 3
-    y = F.conv_transpose2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, stride=2, padding=0)
+    y = F.conv_transpose2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1).contiguous(), b, stride=2, padding=0)
     y = y[:, :, : 2 * h, : 2 * wd]
     if relu:
         y = torch.relu(y)

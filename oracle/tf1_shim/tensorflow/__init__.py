@@ -129,6 +129,17 @@ def reduce_sum(x, axis=None, keepdims=False, name=None):
     return x.sum() if axis is None else x.sum(dim=axis, keepdim=keepdims)
 
 
+def reduce_mean(x, axis=None, keepdims=False, name=None):
+    x = _t(x)
+    return x.mean() if axis is None else x.mean(dim=axis, keepdim=keepdims)
+
+
+def abs(x, name=None): return torch.abs(x)                       # noqa: A001 (mirrors tf.abs)
+
+
+def matrix_inverse(x, name=None): return torch.linalg.inv(x)
+
+
 def count_nonzero(x, name=None):
     return (_t(x) != 0).sum()
 

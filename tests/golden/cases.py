@@ -88,3 +88,26 @@ def label_case(n=1, seed=31):
     nis = np.exp(rng.normal(size=(1, h, w, 3)) * 2.0 - 1.0) * (rng.uniform(size=(1, h, w, 3)) > 0.1)
     return dict(gt=gt, mask=mask, pred=pred, unc=unc, nis=nis)
 
+
+def training_case(seed=41):
+    """4 consecutive small frames; ground truth = the (oracle-computed) measurement map of the synthetic network plus
+    noise of two scales, moved to the world frame -- so that both branches of the loss clamp (KFNet.py:217: only
+    pixels whose unclamped loss is below -2 carry gradient) and of the 5 cm accuracy threshold occur; mask has zeros;
+    poses / pixel map for ReprojectionLoss.  (The oracle only shapes the INPUTS here; the golden outputs come from the
+    reference's code.)"""
+    import torch
+    from oracle import kfnet_oracle as O
+    rng = np.random.default_rng(seed)
+    imgs = small_images(4, seed=seed)
+    h, w = SMALL_HW[0] // 8, SMALL_HW[1] // 8
+    pred = O.scoordnet(imgs, weights(), torch.float64)[0].numpy()
+    scale = np.where(rng.uniform(size=(4, h, w, 1)) > 0.4, 0.004, 0.3)
+    gt_net = pred + rng.normal(size=pred.shape) * scale
+    T = transform()
+    gt_world = gt_net @ T[:3, :3].T + T[:3, 3]
+    mask = (rng.uniform(size=(4, h, w, 1)) > 0.25).astype(np.float64)
+    poses = np.stack([np.linalg.inv(T) for _ in range(4)])
+    poses[:, :3, 3] += rng.normal(size=(4, 3)) * 0.1
+    ys, xs = np.meshgrid(np.linspace(-0.4, 0.4, h), np.linspace(-0.5, 0.5, w), indexing="ij")
+    pixel_map = np.stack([xs, ys], -1)[None].repeat(4, 0)
+    return dict(images=imgs, gt_world=gt_world, mask=mask, poses=poses, pixel_map=pixel_map)

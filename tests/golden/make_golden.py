@@ -81,6 +81,7 @@ def main():
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()})
     metrics(net)
+    training_losses()
 
 
 def metrics(net):
@@ -106,6 +107,34 @@ def metrics(net):
     path = os.path.join(HERE, "kfnet_reference_metrics_on_shim.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: (v.shape, float(v) if v.ndim == 0 else None) for k, v in out.items()})
+
+
+def training_losses():
+    """7. training-graph losses (SURVEY N3), executed from the reference's methods the way train.py::run wires them
+    (train.py:272-296): labels on the 1/8 grid, gt moved by ApplyTransform(..., inverse=True), mask == 1.0,
+    Measure/Temporal/KF CoordLoss with images=resize_images (-> + 50 x SmoothLoss); plus SmoothLoss and
+    ReprojectionLoss on their own."""
+    tc = cases.training_case()
+    imgs = tf.constant(tc["images"])
+    spec = ref_kfnet.KFNetDataSpec(batch_size=4, image_size=tc["images"].shape[1:3])
+    net = ref_kfnet.KFNet(imgs, spec, train_scoordnet=True, train_oflownet=True)
+    h8, w8 = tc["gt_world"].shape[1:3]
+    resize_images = tf.image.resize_nearest_neighbor(imgs, [h8, w8])
+    masks = tf.cast(tf.equal(tf.constant(tc["mask"]), 1.0), tf.float32)
+    T = tf.constant(cases.transform())
+    gt = ref_util.ApplyTransform(tf.constant(tc["gt_world"]), T, inverse=True)
+    out = {"gt_network_frame": npy(gt)}
+    for name, fn in (("measure", net.MeasureCoordLoss), ("temporal", net.TemporalCoordLoss), ("kf", net.KFCoordLoss)):
+        loss, acc = fn(gt, masks, images=resize_images)
+        out[name + "_loss"] = np.asarray(float(loss)); out[name + "_accuracy"] = np.asarray(float(acc))
+    mc, _ = net.GetMeasureCoord()
+    out["smooth_masked"] = np.asarray(float(net.SmoothLoss(mc, resize_images, masks)))
+    out["smooth_nomask"] = np.asarray(float(net.SmoothLoss(mc, resize_images)))
+    out["reproj_masked"] = np.asarray(float(net.ReprojectionLoss(mc, tf.constant(tc["pixel_map"]), tf.constant(tc["poses"]), masks)))
+    out["reproj_nomask"] = np.asarray(float(net.ReprojectionLoss(mc, tf.constant(tc["pixel_map"]), tf.constant(tc["poses"]))))
+    path = os.path.join(HERE, "kfnet_reference_training_on_shim.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: (float(v) if v.ndim == 0 else v.shape) for k, v in out.items()})
 
 
 if __name__ == "__main__":
