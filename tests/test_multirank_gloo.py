@@ -35,7 +35,7 @@ def _worker(rank, world, port, nseq, ret):
 @pytest.mark.parametrize("nseq", [2, 8])
 def test_sequence_sharding_and_single_gather(nseq):
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # (fork from a multi-threaded pytest process is deprecated)
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), nseq, ret), nprocs=world, join=True)
     ref = torch.stack([_fake_eval(s) for s in range(nseq)])
