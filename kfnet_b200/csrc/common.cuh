@@ -70,6 +70,10 @@ struct ConvGeom {
   // fused first layer (tensor-core path, BF16 mode): `in` is the u8 NHWC image [N, IH, IW, 3]; the K = 32 operand row
   // (27 window values - 128, zero padded) is built inside the kernel.  Cin = 32, one tap, stride 1.
   int im2col_u8;
+  // fused difference volume (tensor-core path, BF16 mode, U-Net conv0 on 8x8 windows): `in` is f_prev and `diff_cur`
+  // f_cur, both fp32 [pairs, dGH, dGW, 32]; m-grid row n of the conv = label pixel n over all pairs.
+  const float* diff_cur;
+  int dGH, dGW;
 };
 enum { EPI_NONE = 0, EPI_EXP_CH3 = 1, EPI_L2NORM = 2 };
 

@@ -84,6 +84,13 @@ struct __align__(8) TcParams {
   int im2col;
   const uint8_t* img;
   uint32_t tap_off16[9];        // halo: ((1+dy) * 10*bn + (1+dx)) * row_bytes / 16 per tap
+  // fused difference volume (U-Net conv0, BF16 mode): the halo tile's rows are diff[p,i,j,:] = f_cur[p,:] - f_prev[p + (j-4, i-4),:]
+  // (KFNet.BuildCoordVolume, KFNet.py:343-359; 0 outside the 60x80 map, 0 in the window's halo ring = SAME padding),
+  // rounded to bf16 exactly like diff_volume_kernel, built in shared memory by seven producer warps.
+  int diffp;
+  const float* f_prev;
+  const float* f_cur;
+  int dGH, dGW;
 };
 
 // ------------------------------------------------------------------------------------------ tile iteration
@@ -253,14 +260,15 @@ __device__ __forceinline__ void mma_role_x3(const TcParams& p, uint32_t smem_bas
 // kLean (WIDE / fused-first-layer kernels): plain bf16 layers only -- the bf16x3 accumulator splits, limb outputs,
 // conv2d_transpose phase scatter and special epilogues are compiled out, which shortens the per-tile epilogue chain
 // these layers are bound by and frees registers for the 576 / 672-thread CTAs.
-template <bool kLean, bool kFirst>
+template <bool kLean, int kProd>
 __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
   const int f_x3acc = kLean ? 0 : p.x3acc;
   const int f_out_limbs = kLean ? 1 : p.out_limbs;
   const int f_out_ls = kLean ? 0 : p.out_ls;
   const int f_phase_cout = kLean ? 0 : p.phase_cout;
   const int f_epi = kLean ? (int)EPI_NONE : p.epi;
-  const bool f_im2col = kFirst && p.im2col;     // the im2col producer exists only in conv_tc_kernel_first
+  const bool f_im2col = kProd == 1 && p.im2col;   // the im2col producer exists only in conv_tc_kernel_first
+  const bool f_diff = kProd == 2 && p.diffp;      // the difference-volume producer only in conv_tc_kernel_diff
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full[kMaxStages];
   __shared__ __align__(8) uint64_t s_empty[kMaxStages];
@@ -278,7 +286,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&s_full[s]), f_im2col ? 4u : 1u);   // im2col: one arrival per producer warp
+      mbar_init(smem_u32(&s_full[s]), f_im2col ? 4u : f_diff ? 7u : 1u);   // one arrival per producer warp
       mbar_init(smem_u32(&s_empty[s]), 1);
     }
     for (int a = 0; a < kMaxAcc; ++a) {
@@ -375,6 +383,61 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
 #pragma unroll
       for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(dst + ((q ^ sw) << 4)) = c[q];
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_full[s]));
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
+    }
+  } else if (f_diff && (warp == 0 || warp >= 2 + p.epi_warps)) {
+    // ===================================================================== difference-volume producers (7 warps)
+    // halo tile of two 8x8 windows: rows ordered [y][n][x], y, x in 0..9 (ring = zero padding), n in 0..1
+    const int pq = warp == 0 ? 0 : warp - (1 + p.epi_warps);
+    if (pq == 0 && lane == 0) {
+      const uint32_t wbar = smem_u32(&s_wbar);
+      mbar_expect_tx(wbar, (uint32_t)(p.ntaps * p.kchunks) * p.b_bytes);
+      for (int tap = 0; tap < p.ntaps; ++tap)
+        tma_load_3d(smem_base + (uint32_t)tap * p.w_tile_bytes, &tmB, wbar, 0, 0, tap);
+    }
+    const int r = pq * 32 + lane;
+    const bool rvalid = r < 200;
+    const int y = r / 20, rem = r - y * 20, wn = rem / 10, x = rem - wn * 10;
+    const bool ring = !(y >= 1 && y <= 8 && x >= 1 && x <= 8);
+    uint8_t* const row_ptr = smem_raw + (smem_base - smem_u32(smem_raw)) + p.w_bytes_total + (uint32_t)r * 64u;
+    const int sw = (r >> 1) & 3;
+    const int P = p.dGH * p.dGW;
+    int s = 0;
+    uint32_t ph = 0;
+    TileIter it;
+    for (it.init(p, total_tiles); it.valid(); it.next(p)) {
+      const int window = (it.tn << 1) + wn;                   // label pixel index over all pairs
+      float d[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) d[k] = 0.f;
+      if (rvalid && !ring && window < p.N) {
+        const int pair = window / P, pix = window - pair * P;
+        const int py = pix / p.dGW, px = pix - py * p.dGW;
+        const int sy = py + (y - 1) - 4, sx = px + (x - 1) - 4;    // (i, j) = (y-1, x-1); offsets (ox, oy) = (j-4, i-4)
+        const bool inb = sy >= 0 && sy < p.dGH && sx >= 0 && sx < p.dGW;
+        const float4* cur = reinterpret_cast<const float4*>(p.f_cur + (int64_t)window * 32);
+        const float4* prv = reinterpret_cast<const float4*>(p.f_prev + ((int64_t)pair * P + (inb ? sy * p.dGW + sx : 0)) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 a = __ldg(cur + q);
+          const float4 b = inb ? __ldg(prv + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          d[4 * q + 0] = a.x - b.x; d[4 * q + 1] = a.y - b.y; d[4 * q + 2] = a.z - b.z; d[4 * q + 3] = a.w - b.w;
+        }
+      }
+      uint4 c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        c[q] = make_uint4(pack_bf16(d[8 * q], d[8 * q + 1]), pack_bf16(d[8 * q + 2], d[8 * q + 3]),
+                          pack_bf16(d[8 * q + 4], d[8 * q + 5]), pack_bf16(d[8 * q + 6], d[8 * q + 7]));
+      mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);
+      if (rvalid) {
+        uint8_t* dst = row_ptr + (uint32_t)s * p.stage_bytes;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(dst + ((q ^ sw) << 4)) = c[q];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_full[s]));
       if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -706,27 +769,33 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
 // for the small latency-bound ones, so one CTA's barrier / TMA / TMEM latencies are covered by the other's work.
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  conv_tc_body<false, false>(tmA, tmB, p);
+  conv_tc_body<false, 0>(tmA, tmB, p);
 }
 __global__ void __launch_bounds__(kThreads, 2)
 conv_tc_kernel_x2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  conv_tc_body<false, false>(tmA, tmB, p);
+  conv_tc_body<false, 0>(tmA, tmB, p);
 }
 // co-resident CTAs for plain bf16 layers (most of the U-Net and the tower): the lean body
 __global__ void __launch_bounds__(kThreads, 2)
 conv_tc_kernel_x2_lean(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  conv_tc_body<true, false>(tmA, tmB, p);
+  conv_tc_body<true, 0>(tmA, tmB, p);
 }
 // WIDE: 16 epilogue warps (four groups draining four tiles concurrently) for one-CTA layers with short tiles.
 __global__ void __launch_bounds__(kThreadsWide, 1)
 conv_tc_kernel_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  conv_tc_body<true, false>(tmA, tmB, p);
+  conv_tc_body<true, 0>(tmA, tmB, p);
 }
 
 // Fused first layer: WIDE (or the 320-thread layout) plus three more im2col producer warps.
 __global__ void __launch_bounds__(kThreadsWide + 96, 1)
 conv_tc_kernel_first(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  conv_tc_body<true, true>(tmA, tmB, p);
+  conv_tc_body<true, 1>(tmA, tmB, p);
+}
+
+// U-Net conv0 with the difference volume formed by its own producer warps: WIDE plus six more producer warps.
+__global__ void __launch_bounds__(kThreadsWide + 192, 1)
+conv_tc_kernel_diff(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  conv_tc_body<true, 2>(tmA, tmB, p);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -764,6 +833,10 @@ bool tc_lean_x2_enabled() {
   static const bool on = env_flag("KFN_TC_LEAN_X2", true);
   return on;
 }
+bool tc_diff_fused_enabled() {   // opt-in until validated on hardware
+  static const bool on = env_flag("KFN_TC_DIFF_FUSED", false);
+  return on;
+}
 bool tc_im2col_fused_enabled() {
   static const bool on = env_flag("KFN_TC_IM2COL_FUSED", true);
   return on;
@@ -789,6 +862,10 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   KFN_REQUIRE(g.istride == 1 || (g.istride == 2 && g.IH % 2 == 0 && g.IW % 2 == 0), "stride must be 1 or 2 (even input)");
   KFN_REQUIRE((g.im2col_u8 || (reinterpret_cast<uintptr_t>(in) & 15) == 0) && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
               "TMA needs 16-byte aligned global addresses");
+  if (g.diff_cur)
+    KFN_REQUIRE(g.Cin == 32 && g.ntaps == 9 && g.istride == 1 && g.omul == 1 && g.limbs_w <= 1 && g.limbs_a <= 1 && CoutP <= 128 &&
+                g.IH == 8 && g.IW == 8 && g.MH == 8 && g.MW == 8 && g.dGH > 0 && g.dGW > 0 && !g.im2col_u8 &&
+                (reinterpret_cast<uintptr_t>(g.diff_cur) & 15) == 0, "fused difference volume: conv0 on 8x8 windows");
   if (g.im2col_u8)
     KFN_REQUIRE(g.Cin == 32 && g.ntaps == 1 && g.istride == 1 && g.omul == 1 && g.limbs_w <= 1 && g.limbs_a <= 1 &&
                 CoutP <= 128 && g.IH == g.MH && g.IW == g.MW, "fused first layer shape");
@@ -875,7 +952,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   p.tmem_cols = tmem_cols;
   const uint32_t stage_guess = ((uint32_t)(kBlockM + BN) * row_bytes + 1023u) & ~1023u;
   const bool streaming = g.ntaps == 1 && g.Cin / KC == 1 && (int64_t)g.N * g.MH * g.MW > (1 << 20);   // K=KC 1-tap GEMMs over big maps
-  const bool two_ctas = tc_two_ctas_enabled() && !streaming && !g.im2col_u8 && tmem_cols <= 256 && (12u * stage_guess <= 88u * 1024u || BN <= 64);
+  const bool two_ctas = tc_two_ctas_enabled() && !streaming && !g.im2col_u8 && !g.diff_cur && tmem_cols <= 256 && (12u * stage_guess <= 88u * 1024u || BN <= 64);
   // three CTAs/SM (192 threads, 4 epilogue warps, 56 KB pipeline) for the narrowest layers
   const bool three_ctas = two_ctas && tc_three_ctas_enabled() && tmem_cols <= 128 && 6u * stage_guess <= 56u * 1024u;
   plan->ctas_per_sm = three_ctas ? 3 : two_ctas ? 2 : 1;
@@ -891,6 +968,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   const int64_t mma_cycles = (int64_t)g.ntaps * (g.Cin / KC) * (KC / 16) * (BN / 2 > 48 ? BN / 2 : 48);
   const bool lean_ok = !x3 && g.limbs_out <= 1 && g.phase_cout == 0 && g.epi == EPI_NONE;   // what conv_tc_body<true> keeps
   if (g.im2col_u8) KFN_REQUIRE(lean_ok && plan->ctas_per_sm == 1, "fused first layer: plain bf16 layer, one CTA per SM");
+  if (g.diff_cur) KFN_REQUIRE(lean_ok && plan->ctas_per_sm == 1 && halo && hbn == 2 && KC == 32, "fused difference volume: halo-tile plan");
   const bool wide = tc_wide_enabled() && lean_ok && plan->ctas_per_sm == 1 && BN <= 128 && mma_cycles <= 2500 &&
                     (int64_t)g.N * g.MH * g.MW >= (int64_t)kBlockM * 8 * num_sms;
   p.lg_groups = -1; p.lg_acc = 1;
@@ -926,6 +1004,10 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     p.stages = stages;
     p.epi_stage_off = w_total + (uint32_t)stages * p.stage_bytes;
     plan->smem = (size_t)p.epi_stage_off + (size_t)p.epi_warps * 2048 + 1024;
+    if (g.diff_cur) {   // rows come from the kernel's own producer warps, not from TMA
+      p.diffp = 1; p.f_prev = reinterpret_cast<const float*>(in); p.f_cur = g.diff_cur; p.dGH = g.dGH; p.dGW = g.dGW;
+      plan->threads += 192;
+    }
     // halo view: dims (c, w, n, h, 1) so that the box lands in smem as [y][n][x] rows
     dimA[0] = g.Cin; dimA[1] = g.IW; dimA[2] = g.N; dimA[3] = g.IH; dimA[4] = 1;
     strA[0] = cs; strA[1] = cs * g.IW * g.IH; strA[2] = cs * g.IW; strA[3] = cs * g.IW * g.IH * g.N;
@@ -961,7 +1043,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     }
   }
   CUresult r = CUDA_SUCCESS;
-  if (!g.im2col_u8)   // (the fused first layer has no activation tensor map: tmA stays a copy of tmB, never used)
+  if (!g.im2col_u8 && !g.diff_cur)   // (producer-built A tiles have no activation tensor map: tmA stays a copy of tmB, never used)
     r = encode(tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dimA, strA, boxA, ones,
                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r)); return KFN_ERR_CUDA; }
@@ -972,7 +1054,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   r = encode(tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dimB, strB, boxB, ones,
              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); return KFN_ERR_CUDA; }
-  if (g.im2col_u8) memcpy(tmA, tmB, sizeof(CUtensorMap));
+  if (g.im2col_u8 || g.diff_cur) memcpy(tmA, tmB, sizeof(CUtensorMap));
 
   {
     // prefetch only for memory/latency-bound shapes (few k-blocks per tile); ~384 KB ahead per SM
@@ -1002,6 +1084,7 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
     // WIDE: 184 KB pipeline + 32 KB staging + 1 KB alignment; first layer in the 320-thread layout: 200 + 16 + 1 KB
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_first, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_diff, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     attr_set = true;
   }
   const CUtensorMap* tmA = reinterpret_cast<const CUtensorMap*>(plan.blob);
@@ -1017,7 +1100,9 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
-  if (p.im2col)
+  if (p.diffp)
+    KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_diff, tmA[0], tmA[1], p));
+  else if (p.im2col)
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_first, tmA[0], tmA[1], p));
   else if (plan.threads == kThreadsWide)
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_wide, tmA[0], tmA[1], p));

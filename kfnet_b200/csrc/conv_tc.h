@@ -20,6 +20,7 @@ bool tc_two_ctas_enabled();       // KFN_TC_TWO_CTAS=0: always one CTA per SM (A
 bool tc_three_ctas_enabled();     // KFN_TC_THREE_CTAS=0: at most two CTAs per SM (A/B measurements)
 bool tc_wide_enabled();           // KFN_TC_WIDE: 576-thread four-group epilogue variant for short-tile one-CTA layers
 bool tc_lean_x2_enabled();        // KFN_TC_LEAN_X2: co-resident CTAs of plain bf16 layers run the lean kernel body
+bool tc_diff_fused_enabled();      // KFN_TC_DIFF_FUSED=1 (opt-in, not yet validated): U-Net conv0 forms the difference volume in its producer warps
 bool tc_im2col_fused_enabled();   // KFN_TC_IM2COL_FUSED: BF16 first layers build their im2col rows from the u8 image in-kernel
 bool tc_group2_enabled();         // KFN_TC_GROUP2: two-CTA plans alternate tiles between epilogue halves instead of splitting columns
 bool tc_pdl_enabled();            // KFN_TC_PDL=0: plain stream-ordered launches (A/B measurements)

@@ -248,7 +248,7 @@ int pack_first_both(kfn_handle* h) {
 // 32-wide operand row is built inside the kernel (conv_tc.cu, fused first layer)
 int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff, int MH, int MW, int omul, int oaddy,
            int oaddx, int epi, bool out_fp32, cudaStream_t st, void* out2 = nullptr, int split_col = 0, int out2_cs = 0,
-           bool u8_image = false) {
+           bool u8_image = false, const float* diff_cur = nullptr, int dGH = 0, int dGW = 0) {
   auto it = h->ops.find(key);
   if (it == h->ops.end()) { set_error("unknown op " + key); return KFN_ERR_STATE; }
   const PackedOp& op = it->second;
@@ -268,6 +268,8 @@ int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
   g.phase_cout = op.phase_cout;
   g.split_col = split_col; g.out2_cs = out2_cs;
   g.im2col_u8 = u8_image ? 1 : 0;
+  g.diff_cur = diff_cur; g.dGH = dGH; g.dGW = dGW;   // fused difference volume: in.p is f_prev (fp32)
+  if (diff_cur && h->mode != KFN_MODE_BF16) { set_error(key + ": fused difference volume is BF16-mode only"); return KFN_ERR_ARG; }
   if (u8_image && (h->mode != KFN_MODE_BF16 || op.Cin != 32 || op.ntaps != 1)) {
     set_error(key + ": u8 image input is only valid for the BF16-mode first layers");
     return KFN_ERR_ARG;
@@ -276,7 +278,7 @@ int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
     return launch_conv_simt(g, reinterpret_cast<const float*>(in.p), reinterpret_cast<const float*>(op.w), op.CoutP,
                             op.bias, reinterpret_cast<float*>(out.p), st);
   }
-  const kfn_handle::PlanKey pk(key, (const void*)in.p, out.p, out2,
+  const kfn_handle::PlanKey pk(key, (const void*)in.p, out.p, diff_cur ? (void*)diff_cur : out2,   // (never both)
                                std::array<int, 18>{in.N, in.H, in.W, g.in_cs, MH, MW, out.H, out.W, g.out_cs, out_coff, omul, oaddy,
                                                    oaddx, epi, out_fp32 ? 1 : 0, split_col, out2_cs, g.im2col_u8});
   auto pit = h->plans.find(pk);
@@ -438,12 +440,18 @@ int oflownet_impl(kfn_handle* h, const float* f_prev, const float* f_cur, int NP
   if (ar.overflow) { set_error("workspace too small for oflownet_forward"); return KFN_ERR_WORKSPACE; }
   int rc;
   const int vs = elem_bytes(h);   // bytes per stored element, for channel-offset views
-  if ((rc = launch_diff_volume(f_prev, f_cur, NP, h->GH, h->GW, diff,
-                               h->mode == KFN_MODE_BF16 ? 1 : h->mode == KFN_MODE_BF16X3 ? 3 : 0, st)))
-    return rc;
   const std::string T = "Temporal/";
 #define RUN(x) if ((rc = (x))) return rc
-  RUN(conv(h, T + "conv0", act(diff, R, 8, 8, 32), act(cat0, R, 8, 8, 48), 16, EPI_NONE, false, st));
+  if (h->mode == KFN_MODE_BF16 && tc_diff_fused_enabled()) {
+    // conv0 builds its operand rows f_cur - shifted f_prev itself: the 64x32 volume per label pixel never reaches HBM
+    RUN(run_op(h, T + "conv0", act(const_cast<float*>(f_prev), R, 8, 8, 32, 1), act(cat0, R, 8, 8, 48), 16, 8, 8, 1, 0, 0, EPI_NONE,
+               false, st, nullptr, 0, 0, false, f_cur, h->GH, h->GW));
+  } else {
+    if ((rc = launch_diff_volume(f_prev, f_cur, NP, h->GH, h->GW, diff,
+                                 h->mode == KFN_MODE_BF16 ? 1 : h->mode == KFN_MODE_BF16X3 ? 3 : 0, st)))
+      return rc;
+    RUN(conv(h, T + "conv0", act(diff, R, 8, 8, 32), act(cat0, R, 8, 8, 48), 16, EPI_NONE, false, st));
+  }
   RUN(conv(h, T + "conv1a", act(offs(cat0, 16, vs), R, 8, 8, 48), act(c1a, R, 4, 4, 32), 0, EPI_NONE, false, st));
   RUN(conv(h, T + "conv1b", act(c1a, R, 4, 4, 32), act(cat1, R, 4, 4, 64), 32, EPI_NONE, false, st));
   RUN(conv(h, T + "conv2a", act(offs(cat1, 32, vs), R, 4, 4, 64), act(c2a, R, 2, 2, 64), 0, EPI_NONE, false, st));

@@ -79,3 +79,58 @@ def test_fused_conv1ab_index_model_matches_oracle(shape):
     reff = O.conv2d_same(x, torch.tensor(wf), torch.tensor(bf), 1, True).numpy()
     assert not np.isnan(f1).any()                                  # every pixel is some tile's interior exactly once
     np.testing.assert_allclose(f1, reff, rtol=1e-10, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# conv_tc_kernel_diff (KFN_TC_DIFF_FUSED=1, opt-in): U-Net conv0 whose producer warps form the difference volume.
+def diff_conv0_model(f_prev, f_cur, w, b):
+    """f_prev/f_cur [NP,GH,GW,C]; w [3,3,C,Cout] HWIO.  Mirrors the producer's row numbering (halo tile of two 8x8
+    windows, rows [y][n][x], ring = zeros), the (i, j) -> (oy, ox) = (i-4, j-4) shift with zero fill, and the halo MMA
+    path's tap offsets / 8-row groups pitched by 10*hbn rows."""
+    NP, GH, GW, C = f_cur.shape
+    P, N = GH * GW, NP * GH * GW
+    cout = w.shape[-1]
+    out = np.zeros((N, 8, 8, cout))
+    fp, fc = f_prev.reshape(NP, P, C), f_cur.reshape(N, C)
+    hbn = 2
+    tap_off = [(1 + dy) * 10 * hbn + (1 + dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    for tile in range((N + 1) // 2):
+        A = np.zeros((224, C))
+        for r in range(224):
+            if r >= 200:
+                continue
+            y, rem = divmod(r, 20)
+            wn, x = divmod(rem, 10)
+            window = tile * 2 + wn
+            ring = not (1 <= y <= 8 and 1 <= x <= 8)
+            if ring or window >= N:
+                continue
+            pair, pix = divmod(window, P)
+            py, px = divmod(pix, GW)
+            sy, sx = py + (y - 1) - 4, px + (x - 1) - 4
+            prev = fp[pair, sy * GW + sx] if (0 <= sy < GH and 0 <= sx < GW) else 0.0
+            A[r] = fc[window] - prev
+        acc = np.zeros((128, cout))                     # output row m = (h, n, w): m = h*16 + n*8 + w
+        for t in range(9):
+            ky, kx = divmod(t, 3)
+            rows = [tap_off[t] + (m // 8) * 10 + (m % 8) for m in range(128)]   # 8-row groups pitched by 10 rows
+            acc += A[rows] @ w[ky, kx]
+        for m in range(128):
+            hh, rest = divmod(m, 16)
+            wn, ww = divmod(rest, 8)
+            window = tile * 2 + wn
+            if window < N:
+                out[window, hh, ww] = np.maximum(acc[m] + b, 0.0)
+    return out
+
+
+def test_fused_diff_conv0_index_model_matches_oracle():
+    rng = np.random.default_rng(9)
+    NP, GH, GW, C, cout = 1, 5, 7, 8, 6                 # odd window count: the last tile is half empty
+    f_prev, f_cur = rng.normal(size=(NP, GH, GW, C)), rng.normal(size=(NP, GH, GW, C))
+    w, b = rng.normal(size=(3, 3, C, cout)) * 0.2, rng.normal(size=cout) * 0.1
+    got = diff_conv0_model(f_prev, f_cur, w, b)
+    vol, _ = O.coord_volume(torch.tensor(f_prev), torch.tensor(f_cur))          # [NP,GH,GW,64*C]
+    x = vol.reshape(NP * GH * GW, 8, 8, C)                                      # KFNet.py:372
+    ref = O.conv2d_same(x, torch.tensor(w), torch.tensor(b), 1, True).numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-10)

@@ -30,5 +30,15 @@ if [ $frc -eq 0 ]; then
   KFN_TC_FUSE_CONV1=1 timeout 200 ncu --set full --clock-control none --import-source on -k regex:conv1ab -c 1 -f -o $O/prof_conv1ab \
       python bench.py --steps 1 --warmup 0 --frames 16 --cpu_frames 0 --graph 0 > $O/ncu_full_fused.log 2>&1; echo "ncu full (fused) exit $?"
 fi
+# second opt-in variant: U-Net conv0 forming the difference volume in its producer warps (KFN_TC_DIFF_FUSED=1)
+timeout 100 python tools/ab_compare.py $O/ab_default.npz > $O/ab_default.log 2>&1
+KFN_TC_DIFF_FUSED=1 timeout 100 python tools/ab_compare.py $O/ab_diff.npz $O/ab_default.npz > $O/ab_diff.log 2>&1
+drc=$?; echo "fused difference volume: bit-compare vs default exit $drc"; tail -n 8 $O/ab_diff.log
+if [ $drc -eq 0 ]; then
+  KFN_TC_DIFF_FUSED=1 timeout 300 python -m pytest tests/test_gpu_networks.py tests/test_gpu_properties.py tests/test_gpu_eval_dropin.py -q -m gpu > $O/pytest_diff_paths.log 2>&1
+  echo "network/property/drop-in tests with the fused difference volume exit $?"; tail -n 3 $O/pytest_diff_paths.log
+  b diff_fused KFN_TC_DIFF_FUSED=1
+  b default3 X=1
+fi
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
     python bench.py --steps 1 --warmup 0 --frames 16 --cpu_frames 0 --graph 0 > $O/ncu_list.log 2>&1; echo "ncu list exit $?"
