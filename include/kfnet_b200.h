@@ -50,8 +50,15 @@ enum kfn_status {
  *  KFN_MODE_BF16X3: the same tcgen05 kernel, error-compensated: activations and weights are carried as three bf16
  *                  limbs (x = x1+x2+x3, 24 significant bits) and every layer accumulates the six limb products
  *                  a1w1+a1w2+a2w1+a2w2+a1w3+a3w1 in fp32 TMEM -- fp32-grade results (the 1e-4 parity configs) on
- *                  the tensor cores at 1/6 of the bf16 MMA rate.                                             */
-enum kfn_mode { KFN_MODE_FP32 = 0, KFN_MODE_BF16 = 1, KFN_MODE_BF16X3 = 2 };
+ *                  the tensor cores at 1/6 of the bf16 MMA rate.
+ *  KFN_MODE_FP16X2: error-compensated with TWO fp16 limbs (11 significant bits each): x = x1 + 2^-11 * x2', the second
+ *                  limb stored scaled by 2^11 so that it stays a normal fp16 number; every layer accumulates
+ *                  a1w1 (three TMEM accumulators, round-robin by tap) and a1w2' + a2'w1 (fourth accumulator, scaled
+ *                  by 2^-11 in the epilogue): three MMAs per operand pair instead of six, representation error
+ *                  2^-22 per operand -- the 1e-4 parity configs at 1/3 of the fp16/bf16 MMA rate.  fp16's exponent
+ *                  range bounds activations to |x| < 65504 (true of this network: inputs are (u8-128)*0.00625 and
+ *                  every layer is followed by a ReLU of an O(1) He-scaled sum); BF16X3 is the range-safe mode.   */
+enum kfn_mode { KFN_MODE_FP32 = 0, KFN_MODE_BF16 = 1, KFN_MODE_BF16X3 = 2, KFN_MODE_FP16X2 = 3 };
 
 /* geometry of the path (KFNet/KFNet.py:7-16,70; eval.py:49-50) */
 #define KFN_IMG_H 480
@@ -180,7 +187,8 @@ KFN_API int kfn_eval_sequences_host(kfn_handle* h, const uint8_t* host_images, i
 KFN_API int kfn_conv_layer(kfn_handle* h, const char* op_key, const void* in, int N, int IH, int IW, int in_cs, void* out,
                    int OH, int OW, int out_cs, int out_coff, int out_fp32, int epi, void* stream);
 
-/* Number of kernels this library has launched through this handle since the last call (for bench.py's gpu_launches). */
+/* Number of kernels launched through this handle's entry points since the last reset (bench.py's gpu_launches);
+ * h == NULL: every kernel the calling thread launched through the library, handle-less entry points included. */
 KFN_API int64_t kfn_launch_count(kfn_handle* h, int reset);
 
 #ifdef __cplusplus

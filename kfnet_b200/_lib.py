@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkfnet_b200.so")
 
-KFN_MODE_FP32, KFN_MODE_BF16, KFN_MODE_BF16X3 = 0, 1, 2
+KFN_MODE_FP32, KFN_MODE_BF16, KFN_MODE_BF16X3, KFN_MODE_FP16X2 = 0, 1, 2, 3
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 
 # name -> (restype, argtypes)  -- one entry per KFN_API declaration in include/kfnet_b200.h

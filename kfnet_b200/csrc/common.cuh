@@ -11,7 +11,8 @@
 namespace kfn {
 
 void set_error(const std::string& msg);
-extern thread_local int64_t g_launches;   // kernels launched by this thread through the library
+extern thread_local int64_t g_launches;   // kernels launched by this thread through the library (all handles + handle-less calls)
+extern thread_local int64_t* g_handle_launches;   // counter of the handle whose entry point is running on this thread, or null
 
 #define KFN_CUDA_OK(expr)                                                                          \
   do {                                                                                             \
@@ -25,6 +26,7 @@ extern thread_local int64_t g_launches;   // kernels launched by this thread thr
 #define KFN_LAUNCH_OK()                                                                            \
   do {                                                                                             \
     ++kfn::g_launches;                                                                             \
+    if (kfn::g_handle_launches) ++*kfn::g_handle_launches;                                         \
     cudaError_t _e = cudaGetLastError();                                                           \
     if (_e != cudaSuccess) {                                                                       \
       kfn::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));                     \
@@ -39,6 +41,11 @@ extern thread_local int64_t g_launches;   // kernels launched by this thread thr
       return KFN_ERR_ARG;                                                                          \
     }                                                                                              \
   } while (0)
+
+// Handle-less entry points run on the device that owns their buffers (not on whatever device happens to be current):
+// makes `dev` the current device and returns it through *dev.  SM counts are cached per device.
+int use_device_of(const void* device_ptr, int* dev);
+int sm_count(int dev);
 
 // ---------------------------------------------------------------------------------------------
 // A convolution seen as an implicit GEMM over an "m-grid" of N x MH x MW rows.
@@ -61,6 +68,8 @@ struct ConvGeom {
   // the GEMM accumulates the limb products a1w1 + a1w2 + a2w1 + a2w2 + a1w3 + a3w1 in fp32.
   int limbs_a, limbs_w, limbs_out;
   int in_ls, out_ls;
+  // KFN_MODE_FP16X2: limbs are fp16, x = x1 + 2^-11 * x2' (two limbs; products a1w1 + 2^-11 (a1w2' + a2'w1))
+  int half_limbs;
   // merged conv2d_transpose: output columns [ph*phase_cout, (ph+1)*phase_cout) belong to sub-pixel phase ph = 2*py+px and
   // are written to pixel (my*2 + py, mx*2 + px), channels [out_coff, out_coff + phase_cout).  0 = plain layer.
   int phase_cout;
@@ -83,10 +92,10 @@ int launch_conv_simt(const ConvGeom& g, const float* in, const float* w, int Cou
 
 // pointwise / gather kernels (pointwise.cu)
 int launch_preprocess_f32(const uint8_t* img, float* out, int64_t n, cudaStream_t st);
-int launch_im2col27_bf16(const uint8_t* img, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st);
+int launch_im2col27_bf16(const uint8_t* img, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st, int f16 = 0);
 int launch_l2norm32(float* x, int64_t rows, cudaStream_t st);
 int launch_diff_volume(const float* f_prev, const float* f_cur, int NP, int GH, int GW, void* diff, int out_bf16,
-                       cudaStream_t st);   // out_bf16: 0 fp32, 1 bf16, 3 three bf16 limbs [.., 3, 32]
+                       cudaStream_t st);   // out_bf16: 0 fp32, 1 bf16, 3 three bf16 limbs [.., 3, 32], 2 two fp16 limbs [.., 2, 32] (second scaled by 2^11)
 int launch_softmax_flow(const float* logits, const float* logsig, int logsig_stride, int64_t rows, float* flow,
                         float* sigma_w, int32_t* argmax, cudaStream_t st);
 int launch_kalman_scan(const float* measure, const float* flow, const float* sigma_w, const float* state_in,

@@ -80,7 +80,6 @@ conv1ab_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -107,6 +106,7 @@ conv1ab_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // after the TMEM allocation (see conv_tc.cu)
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp < 6) {

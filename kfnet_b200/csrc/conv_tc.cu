@@ -76,6 +76,8 @@ struct __align__(8) TcParams {
   void* out2;
   int x3acc;                    // 1: four 128-column TMEM accumulators (3 main-term splits + corrections), single-buffered
   int la[6], lw[6];
+  int f16;                      // limbs are fp16 (KFN_MODE_FP16X2): limb 1 holds the residual scaled by 2^11
+  float corr_scale;             // factor applied to the correction accumulator in the epilogue (1, or 2^-11 for fp16 limbs)
   uint32_t epi_stage_off;       // byte offset (from the 1024-aligned smem base) of the epilogue staging area
   // fused first layer (BF16 mode): the A tile is the 32-wide im2col row of the 3x3x3 window, built in shared memory by
   // four producer warps straight from the u8 image (SCoordNet.py:34-37 preprocess: u8 - 128 is exact in bf16, the
@@ -267,6 +269,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
   const int f_out_ls = kLean ? 0 : p.out_ls;
   const int f_phase_cout = kLean ? 0 : p.phase_cout;
   const int f_epi = kLean ? (int)EPI_NONE : p.epi;
+  const bool f_f16 = kLean ? false : (p.f16 != 0);
+  const float f_cs = kLean ? 1.0f : p.corr_scale;
   const bool f_im2col = kProd == 1 && p.im2col;   // the im2col producer exists only in conv_tc_kernel_first
   const bool f_diff = kProd == 2 && p.diffp;      // the difference-volume producer only in conv_tc_kernel_diff
   extern __shared__ uint8_t smem_raw[];
@@ -280,10 +284,6 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  // programmatic dependent launch: let the next kernel's CTAs be scheduled as SMs free up (they run their own
-  // prologue and then block in griddepcontrol.wait until this grid has completed and flushed)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&s_full[s]), f_im2col ? 4u : f_diff ? 7u : 1u);   // one arrival per producer warp
@@ -311,6 +311,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  // programmatic dependent launch: let the next kernel's CTAs be scheduled as SMs free up (they run their own prologue
+  // and then block in griddepcontrol.wait until this grid has completed and flushed).  Issued only AFTER this CTA owns
+  // its TMEM columns: a dependent CTA that became co-resident earlier could take the free columns and then sit in
+  // griddepcontrol.wait while this CTA spins in tcgen05.alloc.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
   // from here on we touch global memory, so wait for the previous grid (no-op without the PDL launch attribute)
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -604,8 +609,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
             for (int acc = 1; acc < 4; ++acc) {
               if (acc < 3 && acc >= n_main) continue;
               tmem_ld32(taddr + (uint32_t)acc * p.acc_stride, r);
+              const float sc = acc == 3 ? f_cs : 1.0f;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
+              for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), sc, v[i]);
             }
           }
 #pragma unroll
@@ -647,8 +653,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
               for (int acc = 1; acc < 4; ++acc) {
                 if (acc < 3 && acc >= n_main) continue;
                 tmem_ld32(taddr + (uint32_t)acc * p.acc_stride + nc, r);
+                const float sc = acc == 3 ? f_cs : 1.0f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
+                for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), sc, v[i]);
               }
             }
 #pragma unroll
@@ -664,8 +671,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
               // stage: row = lane (64 B), 16-byte chunk q at slot q ^ ((lane >> 1) & 3): conflict-free both ways
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const uint32_t w0 = pack_bf16(v[8 * q + 0], v[8 * q + 1]), w1 = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
-                const uint32_t w2 = pack_bf16(v[8 * q + 4], v[8 * q + 5]), w3 = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+                const uint32_t w0 = pack_limb(v[8 * q + 0], v[8 * q + 1], f_f16), w1 = pack_limb(v[8 * q + 2], v[8 * q + 3], f_f16);
+                const uint32_t w2 = pack_limb(v[8 * q + 4], v[8 * q + 5], f_f16), w3 = pack_limb(v[8 * q + 6], v[8 * q + 7], f_f16);
                 *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw_st) << 4)) = make_uint4(w0, w1, w2, w3);
               }
               __syncwarp();
@@ -678,7 +685,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
               __syncwarp();
               if (l + 1 < f_out_limbs) {     // next limb = residual after removing this limb's bf16 value
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] -= __bfloat162float(__float2bfloat16(v[i]));
+                for (int i = 0; i < 32; ++i) v[i] = limb_residual(v[i], f_f16);
               }
             }
           }
@@ -692,8 +699,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
               if (acc < 3 && acc >= n_main) continue;
               float w[16];
               tmem_ld16(taddr + (uint32_t)acc * p.acc_stride + nc, w);
+              const float sc = acc == 3 ? f_cs : 1.0f;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += w[i];
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(w[i], sc, v[i]);
             }
           }
           const int c = col0 + nc;
@@ -723,19 +731,19 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
             for (int l = 0; l < f_out_limbs; ++l) {
               uint8_t* dst = rowbase + ph_off + ((int64_t)cc + (int64_t)l * f_out_ls) * 2;
               if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                uint4 o0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                uint4 o1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                uint4 o0 = make_uint4(pack_limb(v[0], v[1], f_f16), pack_limb(v[2], v[3], f_f16), pack_limb(v[4], v[5], f_f16), pack_limb(v[6], v[7], f_f16));
+                uint4 o1 = make_uint4(pack_limb(v[8], v[9], f_f16), pack_limb(v[10], v[11], f_f16), pack_limb(v[12], v[13], f_f16), pack_limb(v[14], v[15], f_f16));
                 reinterpret_cast<uint4*>(dst)[0] = o0;
                 reinterpret_cast<uint4*>(dst)[1] = o1;
               } else {
                 __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                  if (i < nvalid) d[i] = __float2bfloat16(v[i]);
+                  if (i < nvalid) { const uint32_t b = pack_limb(v[i], 0.f, f_f16); d[i] = *reinterpret_cast<const __nv_bfloat16*>(&b); }
               }
               if (l + 1 < f_out_limbs) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] -= __bfloat162float(__float2bfloat16(v[i]));
+                for (int i = 0; i < 16; ++i) v[i] = limb_residual(v[i], f_f16);
               }
             }
           } else {
@@ -911,6 +919,8 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   auto term = [&](int la_, int lw_) { p.la[p.n_terms] = la_; p.lw[p.n_terms] = lw_; ++p.n_terms; };
   if (limbs_a == 3 && limbs_w == 3) { term(0, 2); term(2, 0); term(1, 1); term(0, 1); term(1, 0); term(0, 0); }
   else if (limbs_a == 1 && limbs_w == 3) { term(0, 2); term(0, 1); term(0, 0); }
+  else if (limbs_a == 2 && limbs_w == 2) { term(0, 1); term(1, 0); term(0, 0); }     // fp16x2: a1*w2' + a2'*w1 (x 2^-11) + a1*w1
+  else if (limbs_a == 1 && limbs_w == 2) { term(0, 1); term(0, 0); }
   else if (limbs_a == 1 && limbs_w == 1) { term(0, 0); }
   else { set_error("unsupported limb combination"); return KFN_ERR_ARG; }
   p.cpk = g.Cin / KC;
@@ -929,7 +939,12 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   const uint32_t sbo16 = (uint32_t)(8 * row_bytes) >> 4;
   p.desc_hi = sbo16 | (1u << 14) | (layout_type << 29);   // bits 32-45 SBO, 46 version=1, 61-63 layout
   p.desc_hi_halo = ((uint32_t)(10 * row_bytes) >> 4) | (1u << 14) | (layout_type << 29);
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  // instruction descriptor: D = f32, A / B format 1 = bf16 (0 = fp16: KFN_MODE_FP16X2), N >> 3, M >> 4
+  const uint32_t ab_fmt = g.half_limbs ? 0u : 1u;
+  p.idesc = (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  p.f16 = g.half_limbs ? 1 : 0;
+  p.corr_scale = g.half_limbs ? 1.0f / 2048.0f : 1.0f;
+  if (g.half_limbs) KFN_REQUIRE(limbs_w == 2 && limbs_a <= 2 && (g.limbs_out <= 2), "fp16 limbs: two-limb weights / activations only");
   p.b_bytes = (uint32_t)(BN * row_bytes);
   p.row_bytes = row_bytes;
   p.OH = g.OH; p.OW = g.OW; p.out_cs = g.out_cs; p.out_coff = g.out_coff; p.Cout = g.Cout;
@@ -966,7 +981,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   // bound it (tensor time per MMA ~ max(BN/2, 48) cycles: N <= 64 is bound by the A-operand fetch from smem).
   // Four accumulator stages of roundup(BN, 32) columns, four epilogue groups, 32 KB of store staging.
   const int64_t mma_cycles = (int64_t)g.ntaps * (g.Cin / KC) * (KC / 16) * (BN / 2 > 48 ? BN / 2 : 48);
-  const bool lean_ok = !x3 && g.limbs_out <= 1 && g.phase_cout == 0 && g.epi == EPI_NONE;   // what conv_tc_body<true> keeps
+  const bool lean_ok = !x3 && !g.half_limbs && g.limbs_out <= 1 && g.phase_cout == 0 && g.epi == EPI_NONE;   // what conv_tc_body<true> keeps
   if (g.im2col_u8) KFN_REQUIRE(lean_ok && plan->ctas_per_sm == 1, "fused first layer: plain bf16 layer, one CTA per SM");
   if (g.diff_cur) KFN_REQUIRE(lean_ok && plan->ctas_per_sm == 1 && halo && hbn == 2 && KC == 32, "fused difference volume: halo-tile plan");
   const bool wide = tc_wide_enabled() && lean_ok && plan->ctas_per_sm == 1 && BN <= 128 && mma_cycles <= 2500 &&

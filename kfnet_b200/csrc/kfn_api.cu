@@ -5,9 +5,12 @@
 #include <cstring>
 #include <array>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
+
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "conv_tc.h"
@@ -15,7 +18,26 @@
 namespace kfn {
 thread_local std::string g_error;
 thread_local int64_t g_launches = 0;
+thread_local int64_t* g_handle_launches = nullptr;
 void set_error(const std::string& msg) { g_error = msg; }
+
+int use_device_of(const void* device_ptr, int* dev) {
+  cudaPointerAttributes a;
+  KFN_CUDA_OK(cudaPointerGetAttributes(&a, device_ptr));
+  KFN_REQUIRE(a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged, "buffer is not device memory");
+  KFN_CUDA_OK(cudaSetDevice(a.device));
+  if (dev) *dev = a.device;
+  return KFN_OK;
+}
+
+int sm_count(int dev) {
+  static std::mutex mu;
+  static int cache[64] = {0};
+  std::lock_guard<std::mutex> lk(mu);
+  int& c = cache[dev & 63];
+  if (!c && cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) c = 148;
+  return c;
+}
 }  // namespace kfn
 
 using namespace kfn;
@@ -63,6 +85,9 @@ struct PackedOp {
   int ntaps = 0, dy[9] = {0}, dx[9] = {0};
   int stride = 1, relu = 0;
   int phase_cout = 0;      // merged conv2d_transpose: Cout per phase (op.Cout = 4 * phase_cout)
+  // taps that can never reach an in-range pixel were dropped for the geometry the op was packed for (m-grid pMH x pMW over
+  // an input of pIH x pIW); `pruned` ops may only run on exactly that geometry
+  int pMH = 0, pMW = 0, pIH = 0, pIW = 0, pruned = 0;
 };
 
 struct Arena {
@@ -92,6 +117,7 @@ struct kfn_handle {
   std::map<PlanKey, TcConvPlan> plans;
   std::map<std::tuple<const void*, void*, void*, int, int, int>, Conv1abPlan> fused_plans;   // (img, out, feat1, N, H, W)
   bool finalized = false;
+  int64_t launches = 0;          // kernels launched through this handle's entry points (kfn_launch_count)
   // kfn_eval_sequences_host: internal copy stream and per-batch events (library-owned)
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> copy_events;
@@ -101,7 +127,9 @@ struct kfn_handle {
 namespace {
 
 // bytes per LOGICAL activation element (allocation) and per STORED element (pointer arithmetic inside a limb)
-int esize(const kfn_handle* h) { return h->mode == KFN_MODE_BF16 ? 2 : h->mode == KFN_MODE_BF16X3 ? 6 : 4; }
+int mode_limbs(const kfn_handle* h) { return h->mode == KFN_MODE_BF16X3 ? 3 : h->mode == KFN_MODE_FP16X2 ? 2 : 1; }   // stored limbs per activation / weight
+bool half_limbs(const kfn_handle* h) { return h->mode == KFN_MODE_FP16X2; }
+int esize(const kfn_handle* h) { return h->mode == KFN_MODE_FP32 ? 4 : 2 * mode_limbs(h); }
 int elem_bytes(const kfn_handle* h) { return h->mode == KFN_MODE_FP32 ? 4 : 2; }
 bool is_tc(const kfn_handle* h) { return h->mode != KFN_MODE_FP32; }
 
@@ -157,9 +185,16 @@ int pack_op(kfn_handle* h, const std::string& key, const LayerSpec& L, int phase
   }
   op.ntaps = (int)taps.size();
   if (op.ntaps == 0 || op.ntaps > 9) { set_error("bad tap count for " + key); return KFN_ERR_ARG; }
+  {
+    int full = 1;
+    if (!first_layer_im2col && L.kind == CONV && L.k == 3) full = 9;
+    else if (L.kind == DECONV) full = phase == 4 ? 4 : ((phase >> 1) ? 1 : 2) * ((phase & 1) ? 1 : 2);
+    op.pMH = MH; op.pMW = MW; op.pIH = IH; op.pIW = IW; op.pruned = op.ntaps < full ? 1 : 0;
+  }
   for (int t = 0; t < op.ntaps; ++t) { op.dy[t] = taps[t].dy; op.dx[t] = taps[t].dx; }
   const bool bf16 = is_tc(h);
-  const int wl = h->mode == KFN_MODE_BF16X3 ? 3 : 1;     // weight limbs
+  const int wl = mode_limbs(h);                          // weight limbs
+  const bool hl = half_limbs(h);                         // fp16 limbs, limb 1 = residual * 2^11
   op.CoutP = bf16 ? tc_cout_padded(op.Cout) : (op.Cout + 3) / 4 * 4;
 
   // element (tap t, ci, co) of the logical [taps][Cin][Cout] operand
@@ -203,9 +238,15 @@ int pack_op(kfn_handle* h, const std::string& key, const LayerSpec& L, int phase
         for (int ci = 0; ci < op.Cin; ++ci) {
           float r = W(t, ci, co);
           for (int l = 0; l < wl; ++l) {
-            const __nv_bfloat16 b = __float2bfloat16(r);
-            pk[(((size_t)t * op.CoutP + co) * wl + l) * op.Cin + ci] = b;
-            r -= __bfloat162float(b);
+            if (hl) {
+              const __half hv = __float2half_rn(r);
+              pk[(((size_t)t * op.CoutP + co) * wl + l) * op.Cin + ci] = *reinterpret_cast<const __nv_bfloat16*>(&hv);
+              r = (r - __half2float(hv)) * 2048.0f;
+            } else {
+              const __nv_bfloat16 b = __float2bfloat16(r);
+              pk[(((size_t)t * op.CoutP + co) * wl + l) * op.Cin + ci] = b;
+              r -= __bfloat162float(b);
+            }
           }
         }
     KFN_CUDA_OK(cudaMalloc(&op.w, nelem * wl * sizeof(__nv_bfloat16)));
@@ -252,14 +293,31 @@ int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
   auto it = h->ops.find(key);
   if (it == h->ops.end()) { set_error("unknown op " + key); return KFN_ERR_STATE; }
   const PackedOp& op = it->second;
+  if (op.pruned && (MH != op.pMH || MW != op.pMW || in.H != op.pIH || in.W != op.pIW)) {
+    set_error(key + ": packed with taps pruned for a " + std::to_string(op.pIH) + "x" + std::to_string(op.pIW) + " input; it cannot run on " +
+              std::to_string(in.H) + "x" + std::to_string(in.W));
+    return KFN_ERR_ARG;
+  }
+  if (omul == 1 && (MH != out.H || MW != out.W || in.H != MH * op.stride || in.W != MW * op.stride) && !u8_image && !diff_cur) {
+    set_error(key + ": output grid must be input / stride");
+    return KFN_ERR_ARG;
+  }
+  if (omul == 2 && (out.H != 2 * MH || out.W != 2 * MW || in.H != MH || in.W != MW)) { set_error(key + ": conv2d_transpose output must be 2x the input"); return KFN_ERR_ARG; }
+  {
+    const int cout_px = op.phase_cout ? op.phase_cout : (split_col ? split_col : op.Cout);
+    if (out_coff < 0 || out_coff + cout_px > out.C) { set_error(key + ": out_coff + Cout exceeds the output channel stride"); return KFN_ERR_ARG; }
+    if (!u8_image && !diff_cur && in.C < op.Cin) { set_error(key + ": input channel stride smaller than Cin"); return KFN_ERR_ARG; }
+  }
   ConvGeom g;
   memset(&g, 0, sizeof(g));
   g.N = in.N; g.MH = MH; g.MW = MW;
-  const bool x3 = h->mode == KFN_MODE_BF16X3;
-  const int la = x3 ? (in.limbs ? in.limbs : 3) : 1;
-  const int lo = (x3 && !out_fp32) ? 3 : 1;
+  const int ml = mode_limbs(h);
+  const bool x3 = ml > 1;
+  const int la = x3 ? (in.limbs ? in.limbs : ml) : 1;
+  const int lo = (x3 && !out_fp32) ? ml : 1;
   g.IH = in.H; g.IW = in.W; g.in_cs = in.C * la; g.Cin = op.Cin;
-  g.limbs_a = la; g.limbs_w = x3 ? 3 : 1; g.limbs_out = lo; g.in_ls = in.C; g.out_ls = out.C;
+  g.limbs_a = la; g.limbs_w = ml; g.limbs_out = lo; g.in_ls = in.C; g.out_ls = out.C;
+  g.half_limbs = half_limbs(h) ? 1 : 0;
   g.istride = op.stride;
   g.ntaps = op.ntaps;
   for (int t = 0; t < op.ntaps; ++t) { g.dy[t] = op.dy[t]; g.dx[t] = op.dx[t]; }
@@ -286,7 +344,7 @@ int run_op(kfn_handle* h, const std::string& key, Act in, Act out, int out_coff,
     TcConvPlan plan;
     int rc = prepare_conv_tc(g, in.p, op.w, op.CoutP, op.bias, out.p, out_fp32 ? 0 : 1, h->num_sms, &plan, out2);
     if (rc != KFN_OK) { set_error(key + ": " + g_error); return rc; }
-    if (h->plans.size() > 4096) h->plans.clear();
+    if (h->plans.size() > 4096) h->plans.erase(h->plans.begin());   // bounded cache: drop one entry, not the working set
     pit = h->plans.emplace(pk, plan).first;
   }
   return launch_conv_tc(pit->second, st);
@@ -353,7 +411,7 @@ int scoordnet_impl(kfn_handle* h, const uint8_t* images, int B, float* measure, 
     else rc = run_op(h, "ScoreNet/conv1a", img, act(bufA, B, H, W, 64), 0, H, W, 1, 0, 0, EPI_NONE, false, st, nullptr, 0, 0, true);
     if (rc) return rc;
   } else {
-    if (!shared_pre && (rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
+    if (!shared_pre && (rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st, half_limbs(h)))) return rc;
     if (feat1_out && h->mode == KFN_MODE_BF16) {
       if ((rc = run_op(h, "first#both", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 64), 0, H, W, 1, 0, 0, EPI_NONE, false, st,
                        feat1_out, 64, 16)))
@@ -396,7 +454,7 @@ int tower_impl(kfn_handle* h, const uint8_t* images, int B, float* feat, Arena& 
                                     H, W, 1, 0, 0, EPI_NONE, false, st, nullptr, 0, 0, true)))
       return rc;
   } else {
-    if (!shared_pre && (rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st))) return rc;
+    if (!shared_pre && (rc = launch_im2col27_bf16(images, (__nv_bfloat16*)pre, B, H, W, st, half_limbs(h)))) return rc;
     if (!feat1_done && (rc = conv(h, "Temporal/feat1", act(pre, B, H, W, 32, 1), act(bufA, B, H, W, 16), 0, EPI_NONE, false, st))) return rc;
   }
   struct Step { const char* name; int div; int c; };
@@ -448,7 +506,7 @@ int oflownet_impl(kfn_handle* h, const float* f_prev, const float* f_cur, int NP
                false, st, nullptr, 0, 0, false, f_cur, h->GH, h->GW));
   } else {
     if ((rc = launch_diff_volume(f_prev, f_cur, NP, h->GH, h->GW, diff,
-                                 h->mode == KFN_MODE_BF16 ? 1 : h->mode == KFN_MODE_BF16X3 ? 3 : 0, st)))
+                                 h->mode == KFN_MODE_BF16 ? 1 : h->mode == KFN_MODE_BF16X3 ? 3 : h->mode == KFN_MODE_FP16X2 ? 2 : 0, st)))
       return rc;
     RUN(conv(h, T + "conv0", act(diff, R, 8, 8, 32), act(cat0, R, 8, 8, 48), 16, EPI_NONE, false, st));
   }
@@ -482,7 +540,7 @@ const char* kfn_last_error(void) { return kfn::g_error.c_str(); }
 
 int kfn_create(kfn_handle** out, int device, int mode, int image_h, int image_w) {
   KFN_REQUIRE(out != nullptr, "null out");
-  KFN_REQUIRE(mode == KFN_MODE_FP32 || mode == KFN_MODE_BF16 || mode == KFN_MODE_BF16X3, "unknown mode");
+  KFN_REQUIRE(mode == KFN_MODE_FP32 || mode == KFN_MODE_BF16 || mode == KFN_MODE_BF16X3 || mode == KFN_MODE_FP16X2, "unknown mode");
   KFN_REQUIRE(image_h > 0 && image_w > 0 && image_h % 8 == 0 && image_w % 8 == 0, "image size must be a multiple of 8");
   int ndev = 0;
   KFN_CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -500,6 +558,7 @@ int kfn_create(kfn_handle** out, int device, int mode, int image_h, int image_w)
 
 int kfn_destroy(kfn_handle* h) {
   if (!h) return KFN_OK;
+  if (kfn::g_handle_launches == &h->launches) kfn::g_handle_launches = nullptr;
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);
@@ -597,7 +656,7 @@ int64_t kfn_workspace_bytes(kfn_handle* h, int frames, int pairs) {
   return need + 4096;
 }
 
-#define KFN_READY(h) do { KFN_REQUIRE(h, "null handle"); if (!h->finalized) { set_error("call kfn_finalize_weights first"); return KFN_ERR_STATE; } KFN_CUDA_OK(cudaSetDevice(h->device)); } while (0)
+#define KFN_READY(h) do { KFN_REQUIRE(h, "null handle"); if (!h->finalized) { set_error("call kfn_finalize_weights first"); return KFN_ERR_STATE; } KFN_CUDA_OK(cudaSetDevice(h->device)); kfn::g_handle_launches = &h->launches; } while (0)
 
 int kfn_scoordnet_forward(kfn_handle* h, const uint8_t* images, int B, float* measure, void* workspace,
                           int64_t workspace_bytes, void* stream) {
@@ -618,6 +677,7 @@ int kfn_oflow_feat_forward(kfn_handle* h, const uint8_t* images, int B, float* f
 int kfn_diff_volume(const float* f_prev, const float* f_cur, int NP, int GH, int GW, void* diff, int out_bf16,
                     void* stream) {
   KFN_REQUIRE(f_prev && f_cur && diff && NP > 0 && GH > 0 && GW > 0, "null/empty argument");
+  if (int rc = use_device_of(diff, nullptr)) return rc;
   return launch_diff_volume(f_prev, f_cur, NP, GH, GW, diff, out_bf16, (cudaStream_t)stream);
 }
 
@@ -634,6 +694,7 @@ int kfn_kalman_scan(const float* measure, const float* flow, const float* sigma_
                     int reinit_period, int nis_gate, float* out_map, float* temp, float* kf, float* nis,
                     int32_t* taps, void* stream) {
   KFN_REQUIRE(measure && flow && sigma_w && transform && out_map, "null argument");
+  if (int rc = use_device_of(out_map, nullptr)) return rc;
   return launch_kalman_scan(measure, flow, sigma_w, state_in, state_out, transform, S, T, GH, GW, first_index,
                             reinit_period, nis_gate, out_map, temp, kf, nis, taps, (cudaStream_t)stream);
 }
@@ -642,6 +703,7 @@ int kfn_flow_warp_kalman(const float* flow, const float* sigma_w, const float* l
                          const float* transform, int GH, int GW, float* temp, float* kf, float* nis, float* out_map,
                          int32_t* taps, void* stream) {
   KFN_REQUIRE(flow && sigma_w && last && measure && transform && out_map, "null argument");
+  if (int rc = use_device_of(out_map, nullptr)) return rc;
   return launch_kalman_scan(measure, flow, sigma_w, last, nullptr, transform, 1, 1, GH, GW, 1, 0, 0, out_map, temp, kf,
                             nis, taps, (cudaStream_t)stream);
 }
@@ -649,16 +711,19 @@ int kfn_flow_warp_kalman(const float* flow, const float* sigma_w, const float* l
 int kfn_bilinear_sampler(const float* imgs, const float* coords, float* out, int N, int H, int W, int C, int Ht, int Wt,
                          void* stream) {
   KFN_REQUIRE(imgs && coords && out && N > 0 && H > 0 && W > 0 && C > 0 && Ht > 0 && Wt > 0, "null/empty argument");
+  if (int rc = use_device_of(out, nullptr)) return rc;
   return launch_bilinear_sampler(imgs, coords, out, N, H, W, C, Ht, Wt, (cudaStream_t)stream);
 }
 
 int kfn_apply_transform(const float* in, float* out, int64_t npix, const float* transform, void* stream) {
   KFN_REQUIRE(in && out && transform && npix > 0, "null/empty argument");
+  if (int rc = use_device_of(out, nullptr)) return rc;
   return launch_apply_transform(in, out, npix, transform, (cudaStream_t)stream);
 }
 
 int kfn_kalman_update(const float* prior, const float* measure, int64_t npix, float* posterior, float* nis, void* stream) {
   KFN_REQUIRE(prior && measure && npix > 0 && (posterior || nis), "null/empty argument");
+  if (int rc = use_device_of(prior, nullptr)) return rc;
   return launch_kalman_update(prior, measure, npix, posterior, nis, (cudaStream_t)stream);
 }
 
@@ -698,7 +763,7 @@ int eval_sequences_impl(kfn_handle* h, const uint8_t* images, int S, int T, cons
     void* pre = fused ? nullptr : a.alloc(h->mode == KFN_MODE_FP32 ? px * 3 * 4 : px * 32 * 2);
     if (a.overflow) { set_error("workspace too small for eval_sequences"); return KFN_ERR_WORKSPACE; }
     if (h->mode == KFN_MODE_FP32) { if ((rc = launch_preprocess_f32(images + f0 * img_bytes, (float*)pre, px * 3, st))) return rc; }
-    else if (!fused) { if ((rc = launch_im2col27_bf16(images + f0 * img_bytes, (__nv_bfloat16*)pre, B, h->H, h->W, st))) return rc; }
+    else if (!fused) { if ((rc = launch_im2col27_bf16(images + f0 * img_bytes, (__nv_bfloat16*)pre, B, h->H, h->W, st, half_limbs(h)))) return rc; }
     static const bool fuse_first = [] { const char* e = getenv("KFN_FUSE_FIRST"); return !(e && e[0] == '0'); }();   // A/B switch
     void* f1 = (h->mode == KFN_MODE_BF16 && fuse_first) ? a.alloc(px * 16 * 2) : nullptr;   // feat1 output, produced by the fused first layer
     if (a.overflow) { set_error("workspace too small for eval_sequences"); return KFN_ERR_WORKSPACE; }
@@ -801,9 +866,11 @@ int kfn_conv_layer(kfn_handle* h, const char* op_key, const void* in, int N, int
 }
 
 int64_t kfn_launch_count(kfn_handle* h, int reset) {
-  (void)h;
-  int64_t v = kfn::g_launches;
-  if (reset) kfn::g_launches = 0;
+  // with a handle: kernels launched by that handle's entry points; with NULL: everything this thread launched through
+  // the library, handle-less entry points included
+  int64_t& c = h ? h->launches : kfn::g_launches;
+  const int64_t v = c;
+  if (reset) c = 0;
   return v;
 }
 

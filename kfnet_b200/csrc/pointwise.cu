@@ -4,6 +4,8 @@
 #include <cooperative_groups.h>
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace kfn {
@@ -28,6 +30,13 @@ int launch_preprocess_f32(const uint8_t* img, float* out, int64_t n, cudaStream_
 // 3x3 SAME im2col of the raw image for the two Cin=3 first layers (SCoordNet conv1a, tower feat1):
 // out[b,y,x, (ky*3+kx)*3 + c] = img[b, y+ky-1, x+kx-1, c] - 128  (0 outside; k = 27..31 zero).
 // u8 - 128 is exact in bf16; the 0.00625 preprocess scale is folded into the packed weights.
+// bf16 or (KFN_MODE_FP16X2) fp16 bit pattern of one stored activation value; -128..127 is exact in both
+template <bool kHalf>
+__device__ __forceinline__ __nv_bfloat16 to_limb(float v) {
+  if constexpr (kHalf) { const __half h = __float2half_rn(v); return *reinterpret_cast<const __nv_bfloat16*>(&h); }
+  else return __float2bfloat16(v);
+}
+template <bool kHalf>
 __global__ void im2col27_bf16_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H,
                                      int W) {
   int64_t total = (int64_t)B * H * W;
@@ -47,20 +56,21 @@ __global__ void im2col27_bf16_kernel(const uint8_t* __restrict__ img, __nv_bfloa
       const uint8_t* p = base + ((int64_t)yy * W + xx) * 3;
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        v[(ky * 3 + kx) * 3 + c] = __float2bfloat16(inb ? (float)p[c] - 128.0f : 0.0f);
+        v[(ky * 3 + kx) * 3 + c] = to_limb<kHalf>(inb ? (float)p[c] - 128.0f : 0.0f);
     }
   }
 #pragma unroll
-  for (int k = 27; k < 32; ++k) v[k] = __float2bfloat16(0.0f);
+  for (int k = 27; k < 32; ++k) v[k] = to_limb<kHalf>(0.0f);
   uint4* dst = reinterpret_cast<uint4*>(out + i * 32);
   const uint4* src = reinterpret_cast<const uint4*>(v);
 #pragma unroll
   for (int q = 0; q < 4; ++q) dst[q] = src[q];
 }
 
-int launch_im2col27_bf16(const uint8_t* img, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st) {
+int launch_im2col27_bf16(const uint8_t* img, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st, int f16) {
   int64_t total = (int64_t)B * H * W;
-  im2col27_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, out, B, H, W);
+  if (f16) im2col27_bf16_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, out, B, H, W);
+  else im2col27_bf16_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, out, B, H, W);
   KFN_LAUNCH_OK();
   return KFN_OK;
 }
@@ -136,7 +146,23 @@ __global__ void __launch_bounds__(256) diff_volume_kernel(const float* __restric
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       uint4 o;
-      if constexpr (kBf16 && LIMBS == 3) {
+      if constexpr (kBf16 && LIMBS == 2) {
+        // fp16x2: two fp16 limbs per (pixel, offset): [limb][32 channels], the second = residual * 2^11
+        float d[8] = {a0.x - b0[it].x, a0.y - b0[it].y, a0.z - b0[it].z, a0.w - b0[it].w,
+                      a1.x - b1[it].x, a1.y - b1[it].y, a1.z - b1[it].z, a1.w - b1[it].w};
+        uint4* base = out + ((np * 64 + it * KSUB + ksub) * 2) * GROUPS + g;
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+          __half2 h0 = __floats2half2_rn(d[0], d[1]), h1 = __floats2half2_rn(d[2], d[3]);
+          __half2 h2 = __floats2half2_rn(d[4], d[5]), h3 = __floats2half2_rn(d[6], d[7]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+          base[l * GROUPS] = o;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = (d[i] - __half2float(__float2half_rn(d[i]))) * 2048.0f;
+        }
+        continue;
+      } else if constexpr (kBf16 && LIMBS == 3) {
         // bf16x3: three limbs per (pixel, offset): [limb][32 channels]
         float d[8] = {a0.x - b0[it].x, a0.y - b0[it].y, a0.z - b0[it].z, a0.w - b0[it].w,
                       a1.x - b1[it].x, a1.y - b1[it].y, a1.z - b1[it].z, a1.w - b1[it].w};
@@ -173,7 +199,9 @@ int launch_diff_volume(const float* f_prev, const float* f_cur, int NP, int GH, 
   const int64_t npix = (int64_t)NP * GH * GW;     // one warp each
   int64_t blocks = (npix + 7) / 8;
   if (blocks > 148 * 64) blocks = 148 * 64;       // grid-stride beyond that; multiple of the SM count
-  if (out_bf16 == 3)
+  if (out_bf16 == 2)
+    diff_volume_kernel<true, 2><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, reinterpret_cast<uint4*>(diff), npix, GH, GW);
+  else if (out_bf16 == 3)
     diff_volume_kernel<true, 3><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, reinterpret_cast<uint4*>(diff), npix, GH, GW);
   else if (out_bf16)
     diff_volume_kernel<true, 1><<<(unsigned)blocks, 256, 0, st>>>(f_prev, f_cur, reinterpret_cast<uint4*>(diff), npix, GH, GW);
@@ -450,13 +478,14 @@ int launch_kalman_scan(const float* measure, const float* flow, const float* sig
                        int reinit_period, int nis_gate, float* out_map, float* temp, float* kf, float* nis,
                        int32_t* taps, cudaStream_t st) {
   KFN_REQUIRE(S > 0 && T > 0 && GH > 0 && GW > 0, "empty scan");
+  // without an incoming state the first frame must re-initialise the filter from the measurement (eval.py:94-101);
+  // otherwise frame 0 would warp an uninitialised shared-memory state
+  KFN_REQUIRE(state_in || (reinit_period > 0 && first_index % reinit_period == 0),
+              "state_in is required unless the first frame is a re-initialisation frame (first_index % reinit_period == 0)");
   static const bool use_cluster = [] { const char* e = getenv("KFN_SCAN_CLUSTER"); return !(e && e[0] == '0'); }();
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev0 = 0;
-    KFN_CUDA_OK(cudaGetDevice(&dev0));
-    KFN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev0));
-  }
+  int dev0 = 0;
+  KFN_CUDA_OK(cudaGetDevice(&dev0));
+  const int num_sms = sm_count(dev0);
   // latency regime only: with many sequences one CTA per sequence already fills the SMs (measured: 148 sequences run
   // 8.2 us/frame-step single-CTA vs 25 us as 592 cluster CTAs; 8 sequences run 7.2 vs 4.8 us/frame)
   if (use_cluster && GH >= 2 * kScanCluster && 2 * S * kScanCluster <= num_sms) {

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -122,6 +123,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// one stored limb pair: bf16, or fp16 (KFN_MODE_FP16X2)
+__device__ __forceinline__ uint32_t pack_limb(float a, float b, bool f16) {
+  if (f16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16(a, b);
+}
+// what the next limb has to carry: bf16 limbs store the plain residual, fp16 limbs the residual scaled by 2^11 (keeps it
+// out of fp16's subnormal range; the GEMM's correction accumulator is scaled back by 2^-11 in the epilogue)
+__device__ __forceinline__ float limb_residual(float v, bool f16) {
+  return f16 ? (v - __half2float(__float2half_rn(v))) * 2048.0f : v - __bfloat162float(__float2bfloat16(v));
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from .synth import weight_shapes
 
-MODES = {"fp32": _lib.KFN_MODE_FP32, "bf16": _lib.KFN_MODE_BF16, "bf16x3": _lib.KFN_MODE_BF16X3}
+MODES = {"fp32": _lib.KFN_MODE_FP32, "bf16": _lib.KFN_MODE_BF16, "bf16x3": _lib.KFN_MODE_BF16X3, "fp16x2": _lib.KFN_MODE_FP16X2}
 
 
 def _ptr(t):
@@ -181,6 +181,9 @@ class Engine:
         dev = measure.device
         for t in (measure, flow, sigma_w):
             assert t.is_contiguous() and t.dtype == torch.float32
+        if state_in is None and not (reinit_period > 0 and first_index % reinit_period == 0):
+            raise ValueError("kalman_scan: state_in is required unless the first frame re-initialises the filter "
+                             "(first_index % reinit_period == 0)")
         Tm = np.ascontiguousarray(np.asarray(transform, dtype=np.float32).reshape(16))
         out = torch.empty(S, T, GH, GW, 4, dtype=torch.float32, device=dev)
         temp = kf = nis = taps = state_out = None

@@ -247,7 +247,7 @@ def main(argv=None):
     ap.add_argument("--scene", default="")
     ap.add_argument("--NIS", action="store_true")
     ap.add_argument("--gpu", type=int, default=0)
-    ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16", "bf16x3", "fp16x2"])
     ap.add_argument("--chunk", type=int, default=16)
     a = ap.parse_args(argv)
     snapshot, _ = get_snapshot(a.model_folder)

@@ -17,14 +17,14 @@ BF16_TOL = 0.12      # bf16 activations through 12 (+7+14) layers; measured valu
 def small(weights):
     gpu_setup()
     from kfnet_b200.engine import Engine
-    return {m: Engine(weights, mode=m, image_size=cases.SMALL_HW) for m in ("fp32", "bf16", "bf16x3")}
+    return {m: Engine(weights, mode=m, image_size=cases.SMALL_HW) for m in ("fp32", "bf16", "bf16x3", "fp16x2")}
 
 
 @pytest.fixture(scope="module")
 def full(weights):
     gpu_setup()
     from kfnet_b200.engine import Engine
-    return {m: Engine(weights, mode=m, image_size=(480, 640)) for m in ("fp32", "bf16", "bf16x3")}
+    return {m: Engine(weights, mode=m, image_size=(480, 640)) for m in ("fp32", "bf16", "bf16x3", "fp16x2")}
 
 
 def _u8(x):
@@ -49,7 +49,7 @@ def test_recursive_step_full_480x640_vs_golden(full, golden):
     from kfnet_b200 import KFNet, KFNetDataSpec
     imgs = cases.full_images()
     lc, lu = (torch.tensor(s, dtype=torch.float32).cuda() for s in cases.full_state())
-    for mode, tol in (("fp32", 1e-4), ("bf16x3", 1e-4), ("bf16", BF16_TOL)):
+    for mode, tol in (("fp32", 1e-4), ("bf16x3", 1e-4), ("fp16x2", 1e-4), ("bf16", BF16_TOL)):
         net = KFNet(_u8(imgs), KFNetDataSpec(batch_size=2), engine=full[mode])
         mc, mu = net.GetMeasureCoord2()
         tc, tu, kc, ku = net.GetKFCoordRecursive(lc, lu)
@@ -108,7 +108,10 @@ def test_eval_sequences_small_vs_oracle(small, weights):
     outx = small["bf16x3"].eval_sequences(dev, Tm, reinit_period=4, frames_per_batch=4, pairs_per_batch=5).cpu()
     ex = assert_close_rms(outx[..., :3], ref[..., :3], 1e-4, "bf16x3 (error-compensated tensor-core) eval out coords")
     assert_close_rms(torch.log(outx[..., 3]), torch.log(ref[..., 3]), 1e-4, "bf16x3 eval out log confidence")
-    print(f"eval_sequences small: fp32 err {e:.2e}/{e2:.2e}, bf16x3 err {ex:.2e}, bf16 err {eb:.2e}")
+    outh = small["fp16x2"].eval_sequences(dev, Tm, reinit_period=4, frames_per_batch=4, pairs_per_batch=5).cpu()
+    eh = assert_close_rms(outh[..., :3], ref[..., :3], 1e-4, "fp16x2 (two fp16 limbs, three products) eval out coords")
+    assert_close_rms(torch.log(outh[..., 3]), torch.log(ref[..., 3]), 1e-4, "fp16x2 eval out log confidence")
+    print(f"eval_sequences small: fp32 err {e:.2e}/{e2:.2e}, bf16x3 err {ex:.2e}, fp16x2 err {eh:.2e}, bf16 err {eb:.2e}")
     # determinism / batch-size independence: different batching gives bit-identical results
     out2 = small["fp32"].eval_sequences(dev, Tm, reinit_period=4, frames_per_batch=12, pairs_per_batch=11).cpu()
     assert torch.equal(out, out2)
@@ -122,6 +125,7 @@ def test_scoordnet_batch8_full_vs_oracle(full, weights):
     m32 = full["fp32"].scoordnet(dev).cpu()
     mbf = full["bf16"].scoordnet(dev).cpu()
     mx3 = full["bf16x3"].scoordnet(dev).cpu()
+    mh2 = full["fp16x2"].scoordnet(dev).cpu()
     for t in (0, 5):
         c64, u64 = O.scoordnet(imgs[t:t + 1].astype(np.float32), weights, torch.float64)
         c32, u32 = O.scoordnet(imgs[t:t + 1].astype(np.float32), weights, torch.float32)
@@ -131,7 +135,9 @@ def test_scoordnet_batch8_full_vs_oracle(full, weights):
         ebf = assert_close_rms(mbf[t:t + 1, ..., :3], c64, BF16_TOL, "bf16 mode coord")
         ex3 = assert_close_rms(mx3[t:t + 1, ..., :3], c64, 1e-4, "bf16x3 mode coord (tcgen05, error-compensated)")
         assert_close_rms(torch.log(mx3[t:t + 1, ..., 3:4]), torch.log(u64), 1e-4, "bf16x3 mode log sigma")
-        print(f"frame {t}: oracle fp32 self-error {e_or:.2e}; fp32 mode {e32:.2e}; bf16x3 mode {ex3:.2e}; bf16 mode {ebf:.2e}")
+        eh2 = assert_close_rms(mh2[t:t + 1, ..., :3], c64, 1e-4, "fp16x2 mode coord (tcgen05, two fp16 limbs)")
+        assert_close_rms(torch.log(mh2[t:t + 1, ..., 3:4]), torch.log(u64), 1e-4, "fp16x2 mode log sigma")
+        print(f"frame {t}: oracle fp32 self-error {e_or:.2e}; fp32 mode {e32:.2e}; bf16x3 mode {ex3:.2e}; fp16x2 mode {eh2:.2e}; bf16 mode {ebf:.2e}")
 
 
 def test_bf16_flow_indices_vs_fp32_mode(full):

@@ -9,7 +9,7 @@ timeout 300 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pyt
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke exit $?"; tail -n 2 $O/smoke.log
 KFN_TC_FUSE_CONV1=1 timeout 120 python -m pytest tests/test_gpu_conv_layers.py -q -m gpu -k fused_conv1ab > $O/t_fused.log 2>&1
 frc=$?; echo "fused conv1ab layer test exit $frc"; tail -n 12 $O/t_fused.log
-b() { name=$1; shift; env "$@" timeout 200 python bench.py --steps 5 --warmup 3 --cpu_frames 0 > $O/bench_$name.json 2> $O/bench_$name.err
+b() { name=$1; shift; env "$@" timeout 200 python bench.py --steps 5 --warmup 3 --cpu_frames 0 --parity_frames 0 --extras 0 --ncu 0 > $O/bench_$name.json 2> $O/bench_$name.err
       python - <<PY
 import json
 try:
@@ -26,9 +26,9 @@ if [ $frc -eq 0 ]; then
   b fused KFN_TC_FUSE_CONV1=1
   b default2 X=1
   KFN_TC_FUSE_CONV1=1 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/launches_fused.csv \
-      python bench.py --steps 1 --warmup 0 --frames 16 --cpu_frames 0 --graph 0 > $O/ncu_list_fused.log 2>&1; echo "ncu list (fused) exit $?"
+      python bench.py --steps 1 --warmup 0 --frames 16 --cpu_frames 0 --graph 0 --parity_frames 0 --extras 0 --ncu 0 > $O/ncu_list_fused.log 2>&1; echo "ncu list (fused) exit $?"
   KFN_TC_FUSE_CONV1=1 timeout 200 ncu --set full --clock-control none --import-source on -k regex:conv1ab -c 1 -f -o $O/prof_conv1ab \
-      python bench.py --steps 1 --warmup 0 --frames 16 --cpu_frames 0 --graph 0 > $O/ncu_full_fused.log 2>&1; echo "ncu full (fused) exit $?"
+      python bench.py --steps 1 --warmup 0 --frames 16 --cpu_frames 0 --graph 0 --parity_frames 0 --extras 0 --ncu 0 > $O/ncu_full_fused.log 2>&1; echo "ncu full (fused) exit $?"
 fi
 # second opt-in variant: U-Net conv0 forming the difference volume in its producer warps (KFN_TC_DIFF_FUSED=1)
 timeout 100 python tools/ab_compare.py $O/ab_default.npz > $O/ab_default.log 2>&1
@@ -41,4 +41,4 @@ if [ $drc -eq 0 ]; then
   b default3 X=1
 fi
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
-    python bench.py --steps 1 --warmup 0 --frames 16 --cpu_frames 0 --graph 0 > $O/ncu_list.log 2>&1; echo "ncu list exit $?"
+    python bench.py --steps 1 --warmup 0 --frames 16 --cpu_frames 0 --graph 0 --parity_frames 0 --extras 0 --ncu 0 > $O/ncu_list.log 2>&1; echo "ncu list exit $?"
