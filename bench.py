@@ -413,6 +413,15 @@ def run_ours(args):
         parity = None
         if world == 1 and args.parity_frames > 0 and args.mode == "bf16":
             parity = parity_block(args, eng, weights, Tm, dev0, T, H, W)
+        dropin = None
+        if world == 1 and args.dropin_frames > 0 and args.mode == "bf16":
+            # the reference-facing eval() from FILES (PNG decode, label reads, metrics, .npy writes included)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import dropin_eval_bench
+                dropin = dropin_eval_bench.run(frames=args.dropin_frames, mode=args.mode, engine=eng)
+            except Exception as e:
+                dropin = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
         cpu = None
         if world == 1 and args.cpu_frames > 0:         # rank 0 at N = 1 only: at N > 1 it would hold the other ranks in a barrier
             loop = ReferenceLoop(args.cpu_frames)
@@ -455,6 +464,7 @@ def run_ours(args):
                           "share_of_step": {"scoordnet": share_sc, "tower": nb_f * t_tw / (ms / args.steps), "oflownet": nb_p * t_of / (ms / args.steps)},
                           "diff_volume_GBps": dv_bytes / t_dv / 1e6, "diff_volume_frac_hbm": dv_bytes / t_dv / 1e6 / pk["hbm"]},
             "parity_mode": parity,
+            "dropin_eval_from_files": dropin,
             "cpu_baseline": cpu,
         }
         line.update(extra)
@@ -481,13 +491,30 @@ def parity_block(args, eng_bf16, weights, Tm, dev_seq, T, H, W):
     oracle_s = time.perf_counter() - t0
     s = ref.pow(2).mean().sqrt()
 
-    def err(e):
-        out = e.eval_sequences(sub.unsqueeze(0), Tm, reinit_period=500, frames_per_batch=n, pairs_per_batch=max(1, n - 1))[0].cpu()
-        return float(((out - ref).abs() / torch.maximum(ref.abs(), s)).max())
+    def run(e):
+        return e.eval_sequences(sub.unsqueeze(0), Tm, reinit_period=500, frames_per_batch=n, pairs_per_batch=max(1, n - 1))[0].cpu()
 
+    def spread(out, r):
+        e = ((out - r).abs() / torch.maximum(r.abs(), r.pow(2).mean().sqrt())).reshape(-1)
+        return {"max": float(e.max()), "p99": float(torch.quantile(e, 0.99)), "median": float(e.median())}
+
+    def err(e):
+        return spread(run(e), ref)["max"]
+
+    # bf16 mode: its distance to the exact oracle, and to the bf16-STORAGE MODEL of the oracle (same roundings at the same
+    # places, oracle/kfnet_quant_oracle.py) -- the second is what the bf16 tests assert (one bf16 ulp on the 99th percentile)
+    from oracle import kfnet_quant_oracle as Q
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        refq = torch.stack([r.out_map for r in Q.eval_sequence(sub.cpu().numpy().astype(np.float32), weights, Tm, seq_len=500)]).float()
+    out_bf16 = run(eng_bf16)
     block = {"tolerance": 1e-4, "error_metric": "max |a-b| / max(|b|, rms(b)) over the output maps [T,60,80,4] (SURVEY 8c) vs the fp64 oracle, "
                                                 "%d full-resolution frames (frame 0 = re-init, %d filtered frames), oracle %.1f s" % (n, n - 1, oracle_s),
-             "bf16_error": err(eng_bf16)}
+             "bf16": {"vs_exact_fp64_oracle": spread(out_bf16, ref), "vs_bf16_storage_model_of_the_oracle": spread(out_bf16, refq),
+                      "storage_model_vs_exact": spread(refq, ref),
+                      "note": "bf16 storage has no tolerance in the reference; the tests hold the kernels to the storage model at 2^-8 "
+                              "(p99; single warped pixels may flip at the sampler edge, which is what the max shows); model run %.1f s"
+                              % (time.perf_counter() - t0)}}
     for mode in args.parity_modes.split(","):
         e = Engine(weights, mode=mode, image_size=(H, W), device=eng_bf16.device)
         out = torch.empty(1, T, e.GH, e.GW, 4, dtype=torch.float32, device="cuda")
@@ -545,6 +572,7 @@ def main():
     ap.add_argument("--cpu_frames", type=int, default=6)
     ap.add_argument("--parity_frames", type=int, default=3, help="frames of the fp64-oracle error check in the parity_mode block (0 = skip)")
     ap.add_argument("--parity_modes", default="fp16x2,bf16x3")
+    ap.add_argument("--dropin_frames", type=int, default=256, help="frames of the drop-in eval()-from-files throughput block (0 = skip)")
     ap.add_argument("--extras", type=int, default=1, help="0: skip the configs4_on_one_gpu / weak / collective / gather-check blocks")
     ap.add_argument("--ncu", type=int, default=1, help="0: skip the ncu dram-bytes pass that fills roofline.traffic")
     ap.add_argument("--graph", type=int, default=1, help="replay each step from a CUDA graph (0 = eager launches)")

@@ -175,6 +175,18 @@ KFN_API int kfn_eval_sequences_host(kfn_handle* h, const uint8_t* host_images, i
                             int reinit_period, int nis_gate, int frames_per_batch, int pairs_per_batch, float* host_out,
                             uint8_t* dev_images, float* dev_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Streaming form for ONE sequence delivered in chunks -- what the drop-in eval() (kfnet_b200/eval.py; reference
+ * KFNet/eval.py:77-126) calls once per chunk of decoded frames: evaluates frames [first_index, first_index + T) from
+ * `host_images` uint8 [T,H,W,3].  The filter state (last_coord, last_uncertainty; eval.py:49-50,102-104) and the feature
+ * map of the chunk's last frame are carried between calls in `carry`: device fp32 [GH*GW*4 | GH*GW*32], caller-owned,
+ * read iff first_index % reinit_period != 0, always written.  host_out fp32 [T,GH,GW,4] as kfn_eval_sequences_host.
+ * host_diag / dev_diag (both or neither): fp32 planar [measure T*P*4 | temp T*P*4 | kf T*P*4 | nis T*P*3], the tensors
+ * eval.py:78-83 fetches for its printed line (temp / kf / nis entries of re-init frames are the measurement / 0). */
+KFN_API int kfn_eval_stream_host(kfn_handle* h, const uint8_t* host_images, int T, int first_index, const float* transform,
+                         int reinit_period, int nis_gate, int frames_per_batch, int pairs_per_batch, float* carry,
+                         float* host_out, float* host_diag, uint8_t* dev_images, float* dev_out, float* dev_diag,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
 /* One packed layer of the path by name (per-layer parity tests and per-layer roofline measurements).
  *   op_key: "<scope>/<layer>" for conv / dense layers, "<scope>/<layer>#p<k>" (k = 2*py+px) for one sub-pixel phase
  *           of a conv2d_transpose, "<scope>/<layer>#all" for all four phases in one GEMM (cnn_wrapper/network.py:116-135, :418-437),
@@ -186,6 +198,28 @@ KFN_API int kfn_eval_sequences_host(kfn_handle* h, const uint8_t* host_images, i
  *   epi   : 0 none, 1 exp on channel 3 (SCoordNet.py:43), 2 l2-normalise 32 channels (KFNet.py:340; BF16 mode only) */
 KFN_API int kfn_conv_layer(kfn_handle* h, const char* op_key, const void* in, int N, int IH, int IW, int in_cs, void* out,
                    int OH, int OW, int out_cs, int out_coff, int out_fp32, int epi, void* stream);
+
+/* ---- training (reference: KFNet/train.py:268-315 `run` + `solver`, KFNet.py:102-146,192-298,430-467) ------------
+ * KFN_MODE_FP32 handles only.  kfn_train_begin copies the loaded weights into the trainable parameter set (device,
+ * TF variable layouts), zeroes the Adam moments and global_step and allocates the activation / gradient arena for windows of
+ * `batch` consecutive frames (reference: 4).  train_scoordnet / train_oflownet mirror KFNet(..., train_scoordnet,
+ * train_oflownet): variables of a frozen scope receive no gradient, no regulariser and no update (train.py:283-285).
+ *
+ * kfn_train_step runs one iteration: forward of SCoordNet / tower / OFlowNet / the unrolled filter (GetKFCoordBatch), the three
+ * losses (CoordLossWithUncertainty + 50 SmoothLoss; 0.2 / 0.2 / 0.6), the whole backward pass, and -- if apply_update --
+ * AdamOptimizer(lr = base_lr * gamma^(global_step / decay_steps)) on loss + l2_regularizer(weight_decay).
+ *   images : device uint8 [batch,H,W,3]      gt8: device fp32 [batch,GH,GW,3] labels ALREADY on the label grid and moved into the
+ *   network's frame (train.py:275-280)         mask8: device fp32 [batch,GH,GW,1] in {0,1}
+ *   scalars_host: HOST fp32 [9] = loss, measure loss, measure accuracy, temporal loss, temporal accuracy, KF loss, KF accuracy,
+ *                 regulariser, learning rate.   The call synchronises `stream`.
+ * kfn_train_get copies one variable (what = 0), its last gradient (1; without the regulariser term) or its Adam m / v (2 / 3)
+ * to host memory by TF variable name.  kfn_train_commit writes the trained parameters back into the handle's weight set and
+ * re-packs the inference operands, so the forward entry points above run the trained network. */
+KFN_API int kfn_train_begin(kfn_handle* h, int batch, int train_scoordnet, int train_oflownet);
+KFN_API int kfn_train_step(kfn_handle* h, const uint8_t* images, const float* gt8, const float* mask8, float base_lr,
+                   float weight_decay, int decay_steps, float gamma, int apply_update, float* scalars_host, void* stream);
+KFN_API int kfn_train_get(kfn_handle* h, const char* name, int what, float* host_out, int64_t n);
+KFN_API int kfn_train_commit(kfn_handle* h);
 
 /* Number of kernels launched through this handle's entry points since the last reset (bench.py's gpu_launches);
  * h == NULL: every kernel the calling thread launched through the library, handle-less entry points included. */

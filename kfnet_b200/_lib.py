@@ -31,7 +31,12 @@ SIGNATURES = {
     "kfn_sequence_extra_bytes": (_i64, [_vp, _i, _i]),
     "kfn_eval_sequences": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "kfn_eval_sequences_host": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "kfn_eval_stream_host": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "kfn_conv_layer": (_i, [_vp, C.c_char_p, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "kfn_train_begin": (_i, [_vp, _i, _i, _i]),
+    "kfn_train_step": (_i, [_vp, _vp, _vp, _vp, C.c_float, C.c_float, _i, C.c_float, _i, _vp, _vp]),
+    "kfn_train_get": (_i, [_vp, C.c_char_p, _i, _vp, _i64]),
+    "kfn_train_commit": (_i, [_vp]),
     "kfn_launch_count": (_i64, [_vp, _i]),
 }
 

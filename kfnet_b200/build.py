@@ -12,7 +12,7 @@ OBJDIR = os.path.join(HERE, "build")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 # pointwise.cu: separate fp32 mul/add rounding like the reference's TF ops (no FMA contraction)
-SOURCES = {"kfn_api.cu": [], "conv_simt.cu": [], "conv_tc.cu": [], "conv1ab_fused.cu": [], "pointwise.cu": ["--fmad=false"]}
+SOURCES = {"kfn_api.cu": [], "conv_simt.cu": [], "conv_tc.cu": [], "conv1ab_fused.cu": [], "pointwise.cu": ["--fmad=false"], "train.cu": []}
 
 
 def _nvcc() -> str:

@@ -83,6 +83,9 @@ struct ConvGeom {
   // f_cur, both fp32 [pairs, dGH, dGW, 32]; m-grid row n of the conv = label pixel n over all pairs.
   const float* diff_cur;
   int dGH, dGW;
+  // fp32 CUDA-core path only (training, train.cu): add the result to what `out` already holds instead of overwriting it
+  // (a gradient that has two consumers, e.g. the U-Net's skip connections)
+  int accum;
 };
 enum { EPI_NONE = 0, EPI_EXP_CH3 = 1, EPI_L2NORM = 2 };
 

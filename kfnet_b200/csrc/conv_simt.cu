@@ -143,7 +143,11 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const SimtParams p) {
       if (g.epi == EPI_EXP_CH3 && (n0 + tn + j) == 3) x = expf(x);
       v[j] = x;
     }
-    if (n0 + tn + 3 < g.Cout && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+    if (g.accum) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n0 + tn + j < g.Cout) dst[j] += v[j];
+    } else if (n0 + tn + 3 < g.Cout && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
       *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
 #pragma unroll

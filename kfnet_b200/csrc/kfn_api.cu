@@ -14,6 +14,8 @@
 
 #include "common.cuh"
 #include "conv_tc.h"
+#include "handle.h"
+#include "layers.h"
 
 namespace kfn {
 thread_local std::string g_error;
@@ -44,52 +46,6 @@ using namespace kfn;
 
 namespace {
 
-enum Kind { CONV = 0, DECONV = 1, DENSE = 2 };
-struct LayerSpec { const char* scope; const char* name; Kind kind; int k, cin, cout, stride; bool relu; };
-
-// cnn_wrapper/SCoordNet.py:21-32, KFNet/KFNet.py:318-338, cnn_wrapper/OFlowNet.py:19-41,50-55
-const LayerSpec kLayers[] = {
-    {"ScoreNet", "conv1a", CONV, 3, 3, 64, 1, true},      {"ScoreNet", "conv1b", CONV, 3, 64, 64, 1, true},
-    {"ScoreNet", "conv2a", CONV, 3, 64, 256, 2, true},    {"ScoreNet", "conv2b", CONV, 3, 256, 256, 1, true},
-    {"ScoreNet", "conv3a", CONV, 3, 256, 512, 2, true},   {"ScoreNet", "conv3b", CONV, 3, 512, 512, 1, true},
-    {"ScoreNet", "conv4a", CONV, 3, 512, 1024, 2, true},  {"ScoreNet", "conv4b", CONV, 3, 1024, 1024, 1, true},
-    {"ScoreNet", "conv5", CONV, 3, 1024, 512, 1, true},   {"ScoreNet", "conv6", CONV, 3, 512, 256, 1, true},
-    {"ScoreNet", "conv7", CONV, 1, 256, 128, 1, true},    {"ScoreNet", "prediction", CONV, 1, 128, 4, 1, false},
-    {"Temporal", "feat1", CONV, 3, 3, 16, 1, true},       {"Temporal", "feat2", CONV, 3, 16, 32, 2, true},
-    {"Temporal", "feat3", CONV, 3, 32, 32, 1, true},      {"Temporal", "feat4", CONV, 3, 32, 64, 2, true},
-    {"Temporal", "feat5", CONV, 3, 64, 64, 1, true},      {"Temporal", "feat6", CONV, 3, 64, 128, 2, true},
-    {"Temporal", "feat7", CONV, 3, 128, 32, 1, false},
-    {"Temporal", "conv0", CONV, 3, 32, 32, 1, true},      {"Temporal", "conv1a", CONV, 3, 32, 32, 2, true},
-    {"Temporal", "conv1b", CONV, 3, 32, 32, 1, true},     {"Temporal", "conv2a", CONV, 3, 32, 64, 2, true},
-    {"Temporal", "conv2b", CONV, 3, 64, 64, 1, true},     {"Temporal", "conv3a", CONV, 3, 64, 128, 2, true},
-    {"Temporal", "conv3b", CONV, 3, 128, 128, 1, true},   {"Temporal", "upconv2", DECONV, 3, 128, 64, 2, true},
-    {"Temporal", "conv4", CONV, 3, 128, 64, 1, true},     {"Temporal", "upconv1", DECONV, 3, 64, 32, 2, true},
-    {"Temporal", "conv5", CONV, 3, 64, 32, 1, true},      {"Temporal", "upconv0", DECONV, 3, 32, 16, 2, true},
-    {"Temporal", "conv6", CONV, 3, 48, 16, 1, true},      {"Temporal", "prediction", CONV, 3, 16, 1, 1, false},
-    {"Temporal", "fc1", DENSE, 1, 128, 64, 1, true},      {"Temporal", "fc2", DENSE, 1, 64, 32, 1, true},
-    {"Temporal", "uncertainty", DENSE, 1, 32, 1, 1, false},
-};
-constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
-
-const LayerSpec* find_layer(const std::string& scope_name) {
-  for (int i = 0; i < kNumLayers; ++i)
-    if (scope_name == std::string(kLayers[i].scope) + "/" + kLayers[i].name) return &kLayers[i];
-  return nullptr;
-}
-
-// One packed GEMM operand: a conv, one phase of a conv2d_transpose, a dense layer, or the im2col'ed first layer.
-struct PackedOp {
-  void* w = nullptr;       // fp32 [ntaps][Cin][CoutP] (FP32 mode) or bf16 [ntaps][CoutP][Cin] (BF16 mode)
-  float* bias = nullptr;   // fp32 [CoutP], zero padded
-  int Cin = 0, Cout = 0, CoutP = 0;
-  int ntaps = 0, dy[9] = {0}, dx[9] = {0};
-  int stride = 1, relu = 0;
-  int phase_cout = 0;      // merged conv2d_transpose: Cout per phase (op.Cout = 4 * phase_cout)
-  // taps that can never reach an in-range pixel were dropped for the geometry the op was packed for (m-grid pMH x pMW over
-  // an input of pIH x pIW); `pruned` ops may only run on exactly that geometry
-  int pMH = 0, pMW = 0, pIH = 0, pIW = 0, pruned = 0;
-};
-
 struct Arena {
   uint8_t* base; int64_t size; int64_t off = 0; bool overflow = false;
   Arena(void* b, int64_t s) : base(reinterpret_cast<uint8_t*>(b)), size(s) {}
@@ -106,23 +62,6 @@ struct Act { void* p; int N, H, W, C; int limbs; };   // NHWC view, C = channels
 
 }  // namespace
 
-struct kfn_handle {
-  int device = 0, mode = 0, H = 0, W = 0, GH = 0, GW = 0, num_sms = 148;
-  std::map<std::string, std::vector<float>> host_w;
-  std::map<std::string, PackedOp> ops;
-  std::vector<void*> allocs;
-  // launch plans (tensor maps + kernel parameters) keyed by op, buffers AND the full geometry: kfn_conv_layer may be
-  // called with different shapes / channel offsets / output types on recycled device pointers
-  typedef std::tuple<std::string, const void*, void*, void*, std::array<int, 18>> PlanKey;
-  std::map<PlanKey, TcConvPlan> plans;
-  std::map<std::tuple<const void*, void*, void*, int, int, int>, Conv1abPlan> fused_plans;   // (img, out, feat1, N, H, W)
-  bool finalized = false;
-  int64_t launches = 0;          // kernels launched through this handle's entry points (kfn_launch_count)
-  // kfn_eval_sequences_host: internal copy stream and per-batch events (library-owned)
-  cudaStream_t copy_stream = nullptr;
-  std::vector<cudaEvent_t> copy_events;
-  cudaEvent_t compute_done = nullptr;
-};
 
 namespace {
 
@@ -560,6 +499,7 @@ int kfn_destroy(kfn_handle* h) {
   if (!h) return KFN_OK;
   if (kfn::g_handle_launches == &h->launches) kfn::g_handle_launches = nullptr;
   cudaSetDevice(h->device);
+  if (h->train) { kfn::train_state_free(h->train); h->train = nullptr; }
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);
   if (h->compute_done) cudaEventDestroy(h->compute_done);
@@ -730,20 +670,35 @@ int kfn_kalman_update(const float* prior, const float* measure, int64_t npix, fl
 int64_t kfn_sequence_extra_bytes(kfn_handle* h, int S, int T) {
   if (!h || S <= 0 || T <= 0) return KFN_ERR_ARG;
   const int64_t F = (int64_t)S * T, P = (int64_t)h->GH * h->GW;
-  return F * P * (4 + 32 + 2 + 1) * 4 + 8 * 1024;
+  return F * P * (4 + 32 + 2 + 1) * 4 + P * 32 * 4 + 8 * 1024;   // + the carried feature slot
 }
 
 }  // extern "C"
 
 namespace {
+// Optional extras of the streaming form (kfn_eval_stream_host): one sequence delivered in chunks.
+struct StreamExtras {
+  int first_index = 0;          // global index of the chunk's first frame (re-init when (first_index + t) % period == 0)
+  float* carry = nullptr;       // device fp32 [P*4 filter state | P*32 features of the previous chunk's last frame], in/out
+  float* measure_out = nullptr; // device fp32 [T,P,4]: use as the measurement buffer (diagnostics) instead of the workspace
+  float* temp = nullptr;        // device fp32 [T,P,4]
+  float* kf = nullptr;          // device fp32 [T,P,4]
+  float* nis = nullptr;         // device fp32 [T,P,3]
+};
+
 // `batch_ready`: optional events, one per frame batch, the compute stream waits on before touching that batch's images
 int eval_sequences_impl(kfn_handle* h, const uint8_t* images, int S, int T, const float* transform, int reinit_period,
                         int nis_gate, int frames_per_batch, int pairs_per_batch, float* out_map, void* workspace,
-                        int64_t workspace_bytes, cudaStream_t st, const cudaEvent_t* batch_ready) {
+                        int64_t workspace_bytes, cudaStream_t st, const cudaEvent_t* batch_ready, const StreamExtras* ex = nullptr) {
   const int64_t F = (int64_t)S * T, P = (int64_t)h->GH * h->GW;
+  const int period = reinit_period > 0 ? reinit_period : (1 << 30);
+  const int first_index = ex ? ex->first_index : 0;
+  // streaming: the chunk continues a sequence iff its first frame is not a re-initialisation frame
+  const bool continues = ex && ex->carry && (first_index % period != 0);
   Arena top(workspace, workspace_bytes);
-  float* measure = (float*)top.alloc(F * P * 4 * 4);
-  float* feat = (float*)top.alloc(F * P * 32 * 4);
+  float* measure = (ex && ex->measure_out) ? ex->measure_out : (float*)top.alloc(F * P * 4 * 4);
+  float* featbuf = (float*)top.alloc((F + 1) * P * 32 * 4);       // slot 0: features of the frame before this chunk
+  float* feat = featbuf + P * 32;
   float* flow = (float*)top.alloc(F * P * 2 * 4);
   float* sigw = (float*)top.alloc(F * P * 4);
   top.alloc(0);
@@ -752,6 +707,7 @@ int eval_sequences_impl(kfn_handle* h, const uint8_t* images, int S, int T, cons
   const int64_t sub_bytes = workspace_bytes - top.off;
   const int64_t img_bytes = (int64_t)h->H * h->W * 3;
   int rc;
+  if (continues) KFN_CUDA_OK(cudaMemcpyAsync(featbuf, ex->carry + P * 4, (size_t)(P * 32 * 4), cudaMemcpyDeviceToDevice, st));
   // 1. measurement system + feature tower: frame-parallel over all S*T frames
   for (int64_t f0 = 0; f0 < F; f0 += frames_per_batch) {
     const int B = (int)((F - f0) < frames_per_batch ? (F - f0) : frames_per_batch);
@@ -772,19 +728,48 @@ int eval_sequences_impl(kfn_handle* h, const uint8_t* images, int S, int T, cons
     a.off = mark;
     if ((rc = tower_impl(h, images + f0 * img_bytes, B, feat + f0 * P * 32, a, st, false, pre, f1))) return rc;
   }
-  // 2. process system: pair (f-1, f) for every flat frame f >= 1.  Pairs that straddle two sequences are computed and
-  //    ignored (frame 0 of every sequence re-initialises the filter, eval.py:94-101).
-  for (int64_t f0 = 1; f0 < F; f0 += pairs_per_batch) {
+  // 2. process system: pair (f-1, f) for every flat frame f >= 1 (f >= 0 when the chunk continues a sequence: slot 0 of
+  //    featbuf then holds frame -1).  Pairs that straddle two sequences are computed and ignored (frame 0 of every
+  //    sequence re-initialises the filter, eval.py:94-101).
+  for (int64_t f0 = continues ? 0 : 1; f0 < F; f0 += pairs_per_batch) {
     const int NP = (int)((F - f0) < pairs_per_batch ? (F - f0) : pairs_per_batch);
     Arena a(sub, sub_bytes);
-    if ((rc = oflownet_impl(h, feat + (f0 - 1) * P * 32, feat + f0 * P * 32, NP, flow + f0 * P * 2, sigw + f0 * P, nullptr,
+    if ((rc = oflownet_impl(h, featbuf + f0 * P * 32, feat + f0 * P * 32, NP, flow + f0 * P * 2, sigw + f0 * P, nullptr,
                             nullptr, a, st, false)))
       return rc;
   }
   // 3. serial scan: warp + Kalman update, one CTA per sequence
-  const int period = reinit_period > 0 ? reinit_period : (1 << 30);
-  return launch_kalman_scan(measure, flow, sigw, nullptr, nullptr, transform, S, T, h->GH, h->GW, 0, period, nis_gate,
-                            out_map, nullptr, nullptr, nullptr, nullptr, st);
+  if ((rc = launch_kalman_scan(measure, flow, sigw, continues ? ex->carry : nullptr, (ex && ex->carry) ? ex->carry : nullptr, transform,
+                               S, T, h->GH, h->GW, first_index, period, nis_gate, out_map, ex ? ex->temp : nullptr,
+                               ex ? ex->kf : nullptr, ex ? ex->nis : nullptr, nullptr, st)))
+    return rc;
+  if (ex && ex->carry)   // features of the chunk's last frame, for the first pair of the next chunk
+    KFN_CUDA_OK(cudaMemcpyAsync(ex->carry + P * 4, feat + (F - 1) * P * 32, (size_t)(P * 32 * 4), cudaMemcpyDeviceToDevice, st));
+  return KFN_OK;
+}
+
+// H2D of the frames batch by batch on the handle's copy stream; fills h->copy_events (one per frame batch)
+int stream_frames_in(kfn_handle* h, const uint8_t* host_images, uint8_t* dev_images, int64_t F, int frames_per_batch, cudaStream_t st) {
+  const int64_t img_bytes = (int64_t)h->H * h->W * 3;
+  const int nb = (int)((F + frames_per_batch - 1) / frames_per_batch);
+  if (!h->copy_stream) KFN_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  if (!h->compute_done) KFN_CUDA_OK(cudaEventCreateWithFlags(&h->compute_done, cudaEventDisableTiming));
+  while ((int)h->copy_events.size() < nb) {
+    cudaEvent_t e;
+    KFN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->copy_events.push_back(e);
+  }
+  // the staging buffer may still be read by work already queued on `st` (previous call): order the copies after it
+  KFN_CUDA_OK(cudaEventRecord(h->compute_done, st));
+  KFN_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->compute_done, 0));
+  for (int b = 0; b < nb; ++b) {
+    const int64_t f0 = (int64_t)b * frames_per_batch;
+    const int64_t nfr = (F - f0) < frames_per_batch ? (F - f0) : frames_per_batch;
+    KFN_CUDA_OK(cudaMemcpyAsync(dev_images + f0 * img_bytes, host_images + f0 * img_bytes, (size_t)(nfr * img_bytes),
+                                cudaMemcpyHostToDevice, h->copy_stream));
+    KFN_CUDA_OK(cudaEventRecord(h->copy_events[b], h->copy_stream));
+  }
+  return KFN_OK;
 }
 }  // namespace
 
@@ -807,29 +792,40 @@ int kfn_eval_sequences_host(kfn_handle* h, const uint8_t* host_images, int S, in
   KFN_REQUIRE(host_images && host_out && dev_images && dev_out && transform && workspace, "null argument");
   KFN_REQUIRE(S > 0 && T > 0 && frames_per_batch > 0 && pairs_per_batch > 0, "empty problem");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t F = (int64_t)S * T, img_bytes = (int64_t)h->H * h->W * 3;
-  const int nb = (int)((F + frames_per_batch - 1) / frames_per_batch);
-  if (!h->copy_stream) KFN_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-  if (!h->compute_done) KFN_CUDA_OK(cudaEventCreateWithFlags(&h->compute_done, cudaEventDisableTiming));
-  while ((int)h->copy_events.size() < nb) {
-    cudaEvent_t e;
-    KFN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    h->copy_events.push_back(e);
-  }
-  // the staging buffer may still be read by work already queued on `st` (previous call): order the copies after it
-  KFN_CUDA_OK(cudaEventRecord(h->compute_done, st));
-  KFN_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->compute_done, 0));
-  for (int b = 0; b < nb; ++b) {
-    const int64_t f0 = (int64_t)b * frames_per_batch;
-    const int64_t nfr = (F - f0) < frames_per_batch ? (F - f0) : frames_per_batch;
-    KFN_CUDA_OK(cudaMemcpyAsync(dev_images + f0 * img_bytes, host_images + f0 * img_bytes, (size_t)(nfr * img_bytes),
-                                cudaMemcpyHostToDevice, h->copy_stream));
-    KFN_CUDA_OK(cudaEventRecord(h->copy_events[b], h->copy_stream));
-  }
-  int rc = eval_sequences_impl(h, dev_images, S, T, transform, reinit_period, nis_gate, frames_per_batch, pairs_per_batch,
-                               dev_out, workspace, workspace_bytes, st, h->copy_events.data());
+  const int64_t F = (int64_t)S * T;
+  int rc = stream_frames_in(h, host_images, dev_images, F, frames_per_batch, st);
+  if (rc != KFN_OK) return rc;
+  rc = eval_sequences_impl(h, dev_images, S, T, transform, reinit_period, nis_gate, frames_per_batch, pairs_per_batch,
+                           dev_out, workspace, workspace_bytes, st, h->copy_events.data());
   if (rc != KFN_OK) return rc;
   KFN_CUDA_OK(cudaMemcpyAsync(host_out, dev_out, (size_t)(F * h->GH * h->GW * 4 * sizeof(float)), cudaMemcpyDeviceToHost, st));
+  KFN_CUDA_OK(cudaStreamSynchronize(st));
+  return KFN_OK;
+}
+
+int kfn_eval_stream_host(kfn_handle* h, const uint8_t* host_images, int T, int first_index, const float* transform,
+                         int reinit_period, int nis_gate, int frames_per_batch, int pairs_per_batch, float* carry,
+                         float* host_out, float* host_diag, uint8_t* dev_images, float* dev_out, float* dev_diag,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+  KFN_READY(h);
+  KFN_REQUIRE(host_images && host_out && dev_images && dev_out && transform && workspace && carry, "null argument");
+  KFN_REQUIRE(T > 0 && first_index >= 0 && frames_per_batch > 0 && pairs_per_batch > 0, "empty problem");
+  KFN_REQUIRE((host_diag == nullptr) == (dev_diag == nullptr), "host_diag and dev_diag go together");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t P = (int64_t)h->GH * h->GW;
+  int rc = stream_frames_in(h, host_images, dev_images, T, frames_per_batch, st);
+  if (rc != KFN_OK) return rc;
+  StreamExtras ex;
+  ex.first_index = first_index; ex.carry = carry;
+  if (dev_diag) {   // planar [measure T*P*4 | temp T*P*4 | kf T*P*4 | nis T*P*3]
+    ex.measure_out = dev_diag; ex.temp = dev_diag + (int64_t)T * P * 4; ex.kf = dev_diag + (int64_t)T * P * 8;
+    ex.nis = dev_diag + (int64_t)T * P * 12;
+  }
+  rc = eval_sequences_impl(h, dev_images, 1, T, transform, reinit_period, nis_gate, frames_per_batch, pairs_per_batch, dev_out,
+                           workspace, workspace_bytes, st, h->copy_events.data(), &ex);
+  if (rc != KFN_OK) return rc;
+  KFN_CUDA_OK(cudaMemcpyAsync(host_out, dev_out, (size_t)(T * P * 4 * sizeof(float)), cudaMemcpyDeviceToHost, st));
+  if (dev_diag) KFN_CUDA_OK(cudaMemcpyAsync(host_diag, dev_diag, (size_t)(T * P * 15 * sizeof(float)), cudaMemcpyDeviceToHost, st));
   KFN_CUDA_OK(cudaStreamSynchronize(st));
   return KFN_OK;
 }

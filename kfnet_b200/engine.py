@@ -109,6 +109,49 @@ class Engine:
                                                     _ptr(dev_out), _ptr(ws), ws.numel(), self._stream()))
         return host_out
 
+    # ---- streaming form for one sequence delivered in chunks (kfn_eval_stream_host; what the drop-in eval() calls) ----
+    def eval_stream_host(self, host_images, first_index, transform, carry=None, reinit_period=500, nis_gate=False,
+                         frames_per_batch=16, pairs_per_batch=16, want_diag=False, capacity=None):
+        """host_images: pinned uint8 [T,H,W,3] = frames first_index .. first_index+T-1 of the stream.  `carry` (device fp32
+        [GH*GW*36]: filter state + last feature map) links consecutive chunks; pass the tensor returned by the previous call.
+        Returns (out_map [T,GH,GW,4] pinned host view, diag dict of host views or None, carry)."""
+        assert host_images.dim() == 4 and host_images.dtype == torch.uint8 and not host_images.is_cuda and host_images.is_contiguous()
+        T = host_images.shape[0]
+        assert tuple(host_images.shape[1:]) == (self.H, self.W, 3)
+        cap = max(int(capacity or 0), T)
+        P = self.GH * self.GW
+        st = getattr(self, "_stream_stage", None)
+        if st is None or st["cap"] < cap:
+            dev = self._dev()
+            st = dict(cap=cap,
+                      dev_imgs=torch.empty(cap, self.H, self.W, 3, dtype=torch.uint8, device=dev),
+                      dev_out=torch.empty(cap * P * 4, dtype=torch.float32, device=dev),
+                      dev_diag=torch.empty(cap * P * 15, dtype=torch.float32, device=dev),
+                      host_out=torch.empty(cap * P * 4, dtype=torch.float32).pin_memory(),
+                      host_diag=torch.empty(cap * P * 15, dtype=torch.float32).pin_memory())
+            self._stream_stage = st
+        if carry is None:
+            carry = torch.zeros(P * 36, dtype=torch.float32, device=self._dev())
+        Tm = np.ascontiguousarray(np.asarray(transform, dtype=np.float32).reshape(16))
+        need = (self.lib.kfn_workspace_bytes(self.h, frames_per_batch, pairs_per_batch)
+                + self.lib.kfn_sequence_extra_bytes(self.h, 1, cap))
+        ws = self._workspace(need)
+        _lib.check(self.lib.kfn_eval_stream_host(
+            self.h, C.c_void_p(host_images.data_ptr()), T, int(first_index), Tm.ctypes.data_as(C.c_void_p), int(reinit_period),
+            1 if nis_gate else 0, int(frames_per_batch), int(pairs_per_batch), _ptr(carry),
+            C.c_void_p(st["host_out"].data_ptr()), C.c_void_p(st["host_diag"].data_ptr()) if want_diag else C.c_void_p(0),
+            _ptr(st["dev_imgs"]), _ptr(st["dev_out"]), _ptr(st["dev_diag"]) if want_diag else C.c_void_p(0),
+            _ptr(ws), ws.numel(), self._stream()))
+        out = st["host_out"][:T * P * 4].view(T, self.GH, self.GW, 4)
+        diag = None
+        if want_diag:
+            d = st["host_diag"]
+            diag = dict(measure=d[:T * P * 4].view(T, self.GH, self.GW, 4),
+                        temp=d[T * P * 4:T * P * 8].view(T, self.GH, self.GW, 4),
+                        kf=d[T * P * 8:T * P * 12].view(T, self.GH, self.GW, 4),
+                        nis=d[T * P * 12:T * P * 15].view(T, self.GH, self.GW, 3))
+        return out, diag, carry
+
     # ---- the same, replayed from a CUDA graph (captured on first use for a given set of buffers / parameters):
     #      removes the CPU launch cost and most of the inter-kernel gaps of the ~7000 launches of a 256-frame step ----
     def eval_sequences_graphed(self, images, transform, out, reinit_period=500, nis_gate=False, frames_per_batch=8,
@@ -208,6 +251,45 @@ class Engine:
         nis = torch.empty(*prior.shape[:-1], 3, dtype=torch.float32, device=prior.device) if want_nis else None
         _lib.check(self.lib.kfn_kalman_update(_ptr(prior), _ptr(measure), npix, _ptr(post), _ptr(nis), self._stream()))
         return post, nis
+
+    # ---- training (kfn_train_*; reference KFNet/train.py `run` + `solver`): FP32-mode engines only ----
+    SCALAR_NAMES = ("loss", "measure_loss", "measure_accuracy", "temporal_loss", "temporal_accuracy", "kf_loss", "kf_accuracy",
+                    "reg_loss", "lr")
+
+    def train_begin(self, batch=4, train_scoordnet=True, train_oflownet=True):
+        if self.mode != "fp32":
+            raise ValueError("training runs on an fp32-mode Engine (the reference's arithmetic)")
+        _lib.check(self.lib.kfn_train_begin(self.h, int(batch), 1 if train_scoordnet else 0, 1 if train_oflownet else 0))
+        self._train_batch = int(batch)
+
+    def train_step(self, images, gt8, mask8, base_lr=1e-4, weight_decay=1e-4, decay_steps=80000, gamma=0.5, apply_update=True):
+        """images: cuda uint8 [B,H,W,3]; gt8: cuda fp32 [B,GH,GW,3] (label grid, network frame); mask8: cuda fp32 [B,GH,GW,1] in {0,1}.
+        Returns the dict of scalars the reference's training loop prints (train.py:370-377) + reg_loss + lr."""
+        B = getattr(self, "_train_batch", None)
+        if B is None:
+            raise RuntimeError("call train_begin first")
+        self._chk_img(images)
+        assert images.shape[0] == B and tuple(gt8.shape) == (B, self.GH, self.GW, 3) and tuple(mask8.shape) == (B, self.GH, self.GW, 1)
+        for t in (gt8, mask8):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        scal = (C.c_float * 9)()
+        _lib.check(self.lib.kfn_train_step(self.h, _ptr(images), _ptr(gt8), _ptr(mask8), float(base_lr), float(weight_decay),
+                                           int(decay_steps), float(gamma), 1 if apply_update else 0, scal, self._stream()))
+        self._graphs = {}          # parameters changed under any captured inference graph once committed
+        return dict(zip(self.SCALAR_NAMES, [float(v) for v in scal]))
+
+    def train_get(self, name, what="param"):
+        """One variable (`param`), its last gradient (`grad`, without the regulariser term) or its Adam moments (`m`, `v`)."""
+        shape = weight_shapes()[name]
+        out = np.empty(shape, dtype=np.float32)
+        _lib.check(self.lib.kfn_train_get(self.h, name.encode(), {"param": 0, "grad": 1, "m": 2, "v": 3}[what],
+                                          out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+    def train_commit(self):
+        """Trained parameters -> the weight set the inference entry points use."""
+        _lib.check(self.lib.kfn_train_commit(self.h))
+        self._graphs = {}
 
     # ---- whole batched eval path on device-resident sequences ----
     def eval_sequences(self, images, transform, reinit_period=500, nis_gate=False, frames_per_batch=8, pairs_per_batch=4,

@@ -157,9 +157,34 @@ def KF_fusion(image_list, label_list, transform, last_coord, last_uncertainty, s
             scal[0], scal[1], scal[2], scal[3], scal[4], scal[5], torch.from_numpy(gt8).to(dev), torch.from_numpy(mask8).to(dev))
 
 
+def load_label8(path, image_size):
+    """The only part of a label eval needs: nearest-neighbour /8 (train.py:259-261) of the raw float32 [H,W,4] file.
+    Memory-mapped so that only the 60 touched rows are read instead of the whole 4.9 MB."""
+    m = np.memmap(path, dtype="<f4", mode="r", shape=(image_size[0], image_size[1], 4))
+    return np.ascontiguousarray(m[::8, ::8])
+
+
+def _frame_metrics(coords, gt, mask):
+    """dist_error (eval.py:17-29) vectorised over a chunk: coords/gt [n,h,w,3], mask [n,h,w,1] -> median cm per frame."""
+    d = np.sqrt(np.square(coords - gt).sum(-1)) * mask[..., 0]
+    d = np.where(d > 0, d, np.nan).reshape(d.shape[0], -1)
+    with np.errstate(all="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", category=RuntimeWarning)
+            return np.nanmedian(d, axis=1) * 100.0
+
+
 def eval(image_list, label_list, transform_file, snapshot, scene="stairs", output_folder="", NIS=False,  # noqa: A001
-         mode="fp32", chunk=16, weights=None, engine=None, quiet=False, device=None):
+         mode="fp32", chunk=64, weights=None, engine=None, quiet=False, device=None, stats=None):
+    """KFNet/eval.py:31-164.  Frames are decoded by a thread pool straight into pinned staging memory one chunk ahead of
+    the GPU; each chunk is ONE C-ABI call (kfn_eval_stream_host: H2D streamed batch by batch, SCoordNet + tower + OFlowNet
+    frame-parallel, the serial warp+Kalman scan, D2H of the output maps and of the tensors the printed line needs), with
+    the filter state and the last feature map carried on the device between chunks.  `stats` (optional dict) receives
+    frames, seconds and frames_per_s of the loop."""
+    import time
     import torch
+    from concurrent.futures import ThreadPoolExecutor
     from .engine import Engine
 
     image_paths, label_paths = read_lines(image_list), read_lines(label_list)
@@ -171,72 +196,133 @@ def eval(image_list, label_list, transform_file, snapshot, scene="stairs", outpu
     if engine is None:
         engine = Engine(weights if weights is not None else load_snapshot_weights(snapshot), mode=mode,
                         image_size=spec.image_size, device=device)
-    dev = torch.device("cuda", engine.device)
-    GH, GW = engine.GH, engine.GW
+    H, W = spec.image_size
     n_iter = len(image_paths)
-    state = None
+    period = spec.sequence_length
+    R, tr = transform[:3, :3], transform[:3, 3]
     dists = [[], [], []]
-    # input pipeline (reference: 1-thread TF queue runner, train.py:203-239): PNG decode / label reads of chunk k+1 run
-    # on a thread pool while the GPU evaluates chunk k (cv2 and numpy file reads release the GIL)
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=max(2, min(32, (os.cpu_count() or 4))))   # ~80-100 PNG decodes/s per core (tools/host_pipeline_bench.py)
+    save_dir = output_folder if (output_folder and os.path.isdir(output_folder)) else None   # eval.py:122
+    # input pipeline (reference: 1-thread TF queue runner, train.py:203-239): ~80-100 PNG decodes/s per core
+    # (tools/host_pipeline_bench.py); cv2 / numpy file reads release the GIL
+    pool = ThreadPoolExecutor(max_workers=max(2, min(64, (os.cpu_count() or 4))))
+    stage = [torch.empty(chunk, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    stage_np = [t.numpy() for t in stage]
 
-    def plan(i0):
+    def decode_into(path, buf, k):
+        import cv2
+        img = cv2.imread(path, cv2.IMREAD_COLOR)
+        if img is None:
+            raise IOError("cannot read image " + path)
+        cv2.cvtColor(img, cv2.COLOR_BGR2RGB, dst=buf[k])          # decode_png(channels=3) order, written into pinned memory
+
+    def plan(ci):
+        i0 = ci * chunk
         its = list(range(i0, min(i0 + chunk, n_iter)))
         pairs = [groups[i % len(groups)] for i in its]
-        frames = sorted({f for p in pairs for f in p})
-        futs_i = [pool.submit(load_image, image_paths[f]) for f in frames]
-        futs_l = [pool.submit(load_label, label_paths[p[1]], spec.image_size) for p in pairs]
-        return its, pairs, frames, futs_i, futs_l
+        buf = stage_np[ci & 1]
+        futs_i = [pool.submit(decode_into, image_paths[p[1]], buf, k) for k, p in enumerate(pairs)]
+        need = sorted({f for p in pairs for f in p})
+        futs_l = {f: pool.submit(load_label8, label_paths[f], spec.image_size) for f in need}
+        return its, pairs, futs_i, futs_l
 
-    starts = list(range(0, n_iter, chunk))
-    nxt = plan(starts[0]) if starts else None
-    for ci, i0 in enumerate(starts):
-        its, pairs, frames, futs_i, futs_l = nxt
-        nxt = plan(starts[ci + 1]) if ci + 1 < len(starts) else None
-        pos = {f: k for k, f in enumerate(frames)}
-        imgs = torch.from_numpy(np.stack([f.result() for f in futs_i])).to(dev)
-        measure_all = engine.scoordnet(imgs)                                               # [F,GH,GW,4]
-        feat_all = engine.oflow_feat(imgs)
-        prev_idx = torch.tensor([pos[p[0]] for p in pairs], device=dev)
-        cur_idx = torch.tensor([pos[p[1]] for p in pairs], device=dev)
-        flow, sigw, _, _ = engine.oflownet(feat_all[prev_idx].contiguous(), feat_all[cur_idx].contiguous())
-        measure = measure_all[cur_idx].unsqueeze(0).contiguous()
-        res = engine.kalman_scan(measure, flow.unsqueeze(0), sigw.unsqueeze(0), transform, state_in=state, first_index=i0,
-                                 reinit_period=spec.sequence_length, nis_gate=NIS, diagnostics=True, want_state=True)
-        state = res["state"]
-        out_map, temp, kf, nis = (res[k][0].cpu().numpy() for k in ("out_map", "temp", "kf", "nis"))
-        meas_np = measure[0].cpu().numpy()
-        for k, i in enumerate(its):
-            prev, index = pairs[k]
-            lab = futs_l[k].result()[::8, ::8]                                             # nearest-neighbour /8 (train.py:259-261)
-            gt, mask = lab[..., :3], lab[..., 3:4]
-            reinit = (i % spec.sequence_length == 0)
-            R, tr = transform[:3, :3], transform[:3, 3]
-            t_meas = meas_np[k, ..., :3] @ R.T + tr
-            t_temp = t_meas if reinit else temp[k, ..., :3] @ R.T + tr
-            d_m, _ = dist_error(t_meas, gt, mask)
-            d_t, _ = dist_error(t_temp, gt, mask)
-            d_kf, _ = dist_error(out_map[k, ..., :3], gt, mask)
-            for lst, v in zip(dists, (d_m, d_t, d_kf)):
-                lst.append(v)
-            if not quiet:
-                l_m, a_m = coord_loss_with_uncertainty(meas_np[k, ..., :3], meas_np[k, ..., 3:4], gt, mask, transform)
-                l_t, a_t = coord_loss_with_uncertainty(temp[k, ..., :3], temp[k, ..., 3:4], gt, mask, transform)
-                l_k, a_k = coord_loss_with_uncertainty(kf[k, ..., :3], kf[k, ..., 3:4], gt, mask, transform)
-                if reinit:
+    # the chunked stream evaluates pair (frame k-1, frame k) of the decoded frames; that is the reference's pair stream
+    # (train.py:67-71) whenever every non-re-init iteration's first frame is the previous iteration's second frame
+    def consecutive(its, pairs, last_cur):
+        prev = last_cur
+        for i, p in zip(its, pairs):
+            if i % period != 0 and p[0] != prev:
+                return False
+            prev = p[1]
+        return True
+
+    n_chunks = (n_iter + chunk - 1) // chunk
+    nxt = plan(0) if n_chunks else None
+    carry, last_cur, state = None, None, None
+    t_start = time.perf_counter()
+    for ci in range(n_chunks):
+        its, pairs, futs_i, futs_l = nxt
+        for f in futs_i:
+            f.result()
+        host_imgs = stage[ci & 1][:len(its)]
+        nxt = plan(ci + 1) if ci + 1 < n_chunks else None           # decode chunk ci+1 while the GPU runs chunk ci
+        if consecutive(its, pairs, last_cur):
+            out_t, diag, carry = engine.eval_stream_host(host_imgs, its[0], transform, carry, reinit_period=period, nis_gate=NIS,
+                                                         want_diag=True, capacity=chunk)
+            out_map = out_t.numpy()
+            meas_np, temp, kf, nis = (diag[k].numpy() for k in ("measure", "temp", "kf", "nis"))
+        else:
+            out_map, meas_np, temp, kf, nis, carry = _eval_chunk_general(engine, host_imgs, pairs, its[0], transform, carry, period, NIS)
+        last_cur = pairs[-1][1]
+        lab = {f: fut.result() for f, fut in futs_l.items()}
+        gt = np.stack([lab[p[1]][..., :3] for p in pairs])
+        mask = np.stack([lab[p[1]][..., 3:4] for p in pairs])
+        reinit = np.array([(i % period == 0) for i in its])
+        t_meas = meas_np[..., :3] @ R.T + tr
+        t_temp = np.where(reinit[:, None, None, None], t_meas, temp[..., :3] @ R.T + tr)
+        d_m, d_t, d_kf = _frame_metrics(t_meas, gt, mask), _frame_metrics(t_temp, gt, mask), _frame_metrics(out_map[..., :3], gt, mask)
+        for lst, v in zip(dists, (d_m, d_t, d_kf)):
+            lst.extend(float(x) for x in v)
+        if not quiet:
+            for k, i in enumerate(its):
+                prev, index = pairs[k]
+                # the reference scores the ONE estimated frame against BOTH ground-truth frames of its batch-of-2
+                # (KFNet.CoordLossWithUncertainty broadcasts [1,60,80,3] against [2,60,80,3]; KFNet.py:214, train.py:250-255)
+                gt2 = np.stack([lab[prev][..., :3], lab[index][..., :3]])
+                mask2 = np.stack([lab[prev][..., 3:4], lab[index][..., 3:4]])
+                l_m, a_m = coord_loss_with_uncertainty(meas_np[k:k + 1, ..., :3], meas_np[k:k + 1, ..., 3:4], gt2, mask2, transform)
+                l_t, a_t = coord_loss_with_uncertainty(temp[k:k + 1, ..., :3], temp[k:k + 1, ..., 3:4], gt2, mask2, transform)
+                l_k, a_k = coord_loss_with_uncertainty(kf[k:k + 1, ..., :3], kf[k:k + 1, ..., 3:4], gt2, mask2, transform)
+                if reinit[k]:
                     print("Reinitialize at the begin of a new sequence.")
                 print("%d, frame %d~%d, l_m = %.3f, l_t = %.3f, l_kf = %.3f, a_m = %.3f, a_t = %.3f, a_kf = %.3f, "
                       "d_m = %.3f, d_t = %.3f, d_kf = %.3f, nis = %.3f"
-                      % (i, prev, index, l_m, l_t, l_k, a_m, a_t, a_k, d_m, d_t, d_kf, get_NIS_measurement(nis[k])))
-            if output_folder and os.path.isdir(output_folder):                             # eval.py:122-126
-                np.save(os.path.join(output_folder, "coord_" + str(index) + ".npy"), out_map[k].astype(np.float32))
-    pool.shutdown(wait=False)
+                      % (i, prev, index, l_m, l_t, l_k, a_m, a_t, a_k, d_m[k], d_t[k], d_kf[k], get_NIS_measurement(nis[k])))
+        if save_dir:                                                                       # eval.py:122-126
+            maps = out_map.astype(np.float32, copy=True)
+            for k, p in enumerate(pairs):
+                pool.submit(np.save, os.path.join(save_dir, "coord_" + str(p[1]) + ".npy"), maps[k])
+    pool.shutdown(wait=True)
+    dt = time.perf_counter() - t_start
+    if stats is not None:
+        stats.update(frames=n_iter, seconds=dt, frames_per_s=n_iter / dt if dt > 0 else float("nan"))
     if not quiet:
         print("Median dist error: ", *[np.median(d) for d in dists])
         print("Mean dist error: ", *[np.mean(d) for d in dists])
         print("stddev error: ", *[np.std(d) for d in dists])
     return dists
+
+
+def _eval_chunk_general(engine, host_imgs, pairs, i0, transform, carry, period, NIS):
+    """Arbitrary pair lists (image lists that wrap around the scene's ranges): the stage APIs with explicit pair gathers.
+    `carry` holds the filter state in its first GH*GW*4 floats exactly like the streaming call."""
+    import torch
+    dev = torch.device("cuda", engine.device)
+    P = engine.GH * engine.GW
+    frames = sorted({f for p in pairs for f in p})
+    # frames of the chunk that are not the second frame of a pair must be decoded here (rare path)
+    cur_pos = {p[1]: k for k, p in enumerate(pairs)}
+    imgs = {f: host_imgs[cur_pos[f]] for f in frames if f in cur_pos}
+    missing = [f for f in frames if f not in imgs]
+    if missing:
+        raise ValueError("eval: image list order needs frames %r that are not part of this chunk's stream" % missing[:4])
+    order = list(imgs)
+    pos = {f: k for k, f in enumerate(order)}
+    batch = torch.stack([imgs[f] for f in order]).to(dev)
+    measure_all = engine.scoordnet(batch)
+    feat_all = engine.oflow_feat(batch)
+    prev_idx = torch.tensor([pos[p[0]] for p in pairs], device=dev)
+    cur_idx = torch.tensor([pos[p[1]] for p in pairs], device=dev)
+    flow, sigw, _, _ = engine.oflownet(feat_all[prev_idx].contiguous(), feat_all[cur_idx].contiguous())
+    measure = measure_all[cur_idx].unsqueeze(0).contiguous()
+    if carry is None:
+        carry = torch.zeros(P * 36, dtype=torch.float32, device=dev)
+    state = carry[:P * 4].view(1, engine.GH, engine.GW, 4) if i0 % period != 0 else None
+    res = engine.kalman_scan(measure, flow.unsqueeze(0), sigw.unsqueeze(0), transform, state_in=state, first_index=i0,
+                             reinit_period=period, nis_gate=NIS, diagnostics=True, want_state=True)
+    carry[:P * 4] = res["state"].reshape(-1)
+    carry[P * 4:] = feat_all[cur_idx[-1]].reshape(-1)
+    out_map, temp, kf, nis = (res[k][0].cpu().numpy() for k in ("out_map", "temp", "kf", "nis"))
+    return out_map, measure[0].cpu().numpy(), temp, kf, nis, carry
 
 
 def main(argv=None):
@@ -248,12 +334,13 @@ def main(argv=None):
     ap.add_argument("--NIS", action="store_true")
     ap.add_argument("--gpu", type=int, default=0)
     ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16", "bf16x3", "fp16x2"])
-    ap.add_argument("--chunk", type=int, default=16)
+    ap.add_argument("--chunk", type=int, default=64)
+    ap.add_argument("--quiet", action="store_true", help="no per-frame line / summary (the output .npy files are unchanged)")
     a = ap.parse_args(argv)
     snapshot, _ = get_snapshot(a.model_folder)
     eval(os.path.join(a.input_folder, "image_list.txt"), os.path.join(a.input_folder, "label_list.txt"),
          os.path.join(a.input_folder, "transform.txt"), snapshot, scene=a.scene, output_folder=a.output_folder,
-         NIS=a.NIS, mode=a.mode, chunk=a.chunk, device=a.gpu)
+         NIS=a.NIS, mode=a.mode, chunk=a.chunk, device=a.gpu, quiet=a.quiet)
 
 
 if __name__ == "__main__":

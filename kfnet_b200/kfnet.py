@@ -14,8 +14,8 @@ _IDENTITY = np.eye(4, dtype=np.float32)
 class KFNet:
     def __init__(self, images, spec, train_scoordnet=False, train_oflownet=False, dropout_rate=0.5, seed=None,
                  reuse=None, *, weights=None, engine: Engine | None = None, mode="fp32"):
-        if train_scoordnet or train_oflownet:
-            raise NotImplementedError("training graphs are outside the built path (SURVEY 8f N3)")
+        # training graphs (KFNet.py:55-63; train.py:283-285): the losses below run the fp32 training path (kfn_train_step)
+        self.train_scoordnet, self.train_oflownet = bool(train_scoordnet), bool(train_oflownet)
         self.focal_x, self.focal_y, self.u, self.v = spec.focal_x, spec.focal_y, spec.u, spec.v
         self.batch_size = spec.batch_size
         self.height, self.width = spec.image_size
@@ -77,6 +77,32 @@ class KFNet:
         t, k = r["temp"][0], r["kf"][0]
         assert t.shape[0] == B
         return t[..., :3], t[..., 3:4], k[..., :3], k[..., 3:4]
+
+    # ---------------------------------------------------------------- losses (KFNet.py:192-298; train.py:287-296)
+    def _losses(self, gt_coords, mask):
+        """Forward of the training graph on this window (no parameter update): dict of the scalars train.py:`run` returns."""
+        key = (gt_coords.data_ptr(), mask.data_ptr())
+        if getattr(self, "_loss_cache", (None, None))[0] != key:
+            if getattr(self.engine, "_train_batch", None) != self.batch_size:
+                self.engine.train_begin(self.batch_size, self.train_scoordnet, self.train_oflownet)
+            out = self.engine.train_step(self.images, gt_coords.float().contiguous(), mask.float().contiguous(), apply_update=False)
+            self._loss_cache = (key, out)
+        return self._loss_cache[1]
+
+    def MeasureCoordLoss(self, gt_coords, mask, transform=None, pixel_map=None, poses=None, images=None):   # KFNet.py:234-255
+        assert transform is None and pixel_map is None and poses is None, "train.py passes images= only (train.py:287-292)"
+        o = self._losses(gt_coords, mask)
+        return o["measure_loss"], o["measure_accuracy"]
+
+    def TemporalCoordLoss(self, gt_coords, mask, transform=None, pixel_map=None, poses=None, images=None):  # KFNet.py:257-279
+        assert transform is None and pixel_map is None and poses is None
+        o = self._losses(gt_coords, mask)
+        return o["temporal_loss"], o["temporal_accuracy"]
+
+    def KFCoordLoss(self, gt_coords, mask, transform=None, pixel_map=None, poses=None, images=None):        # KFNet.py:281-300
+        assert transform is None and pixel_map is None and poses is None
+        o = self._losses(gt_coords, mask)
+        return o["kf_loss"], o["kf_accuracy"]
 
     # ---------------------------------------------------------------- pointwise API surface (kfn_kalman_update)
     def BuildKFCoord(self, last_coord, last_uncertainty, measure_coord, measure_uncertainty):   # KFNet.py:148-162

@@ -1,0 +1,138 @@
+"""Drop-in for the training side of the reference's KFNet/train.py: `run` (losses of one 4-frame window, train.py:268-298),
+`solver` (L2 regulariser + exponential learning-rate decay + AdamOptimizer, train.py:300-315) and the `train` loop
+(train.py:347-420), on the fp32 training path of libkfnet_b200 (kfn_train_begin / kfn_train_step; csrc/train.cu).
+
+Where the reference builds a TF graph once and pulls windows off an input queue, this module evaluates eagerly: one
+`Trainer.step(images, gt_coords, masks)` = forward + losses + backward + Adam on one window.
+
+Usage:  python -m kfnet_b200.train --input_folder D --model_folder M --scene S [--max_steps N] [--fix_flownet]
+"""
+from __future__ import annotations
+
+import argparse
+import os
+
+import numpy as np
+
+from .spec import KFNetDataSpec
+
+# flag defaults of KFNet/train.py:14-47
+BASE_LR, WEIGHT_DECAY, GAMMA, SNAPSHOT, DISPLAY = 1e-4, 1e-4, 0.5, 5000, 10
+STEPVALUE = {"chess": 100000, "fire": 30000, "heads": 60000, "office": 100000, "pumpkin": 100000, "redkitchen": 100000,
+             "stairs": 100000}     # set_stepvalue (train.py:329-345); max_steps = 5 * stepvalue (train.py:349)
+_TRAIN_RANGES = {  # scene -> [start, end) TRAINING ranges (train.py:75-141, is_training=True branches)
+    "chess": [(0, 1000), (1000, 2000), (2000, 3000), (3000, 4000)], "fire": [(0, 1000), (1000, 2000)], "heads": [(0, 1000)],
+    "office": [(i, i + 1000) for i in range(0, 6000, 1000)], "pumpkin": [(0, 1000), (1000, 2000), (2000, 3000), (3000, 4000)],
+    "redkitchen": [(i, i + 1000) for i in range(0, 7000, 1000)], "stairs": [(0, 500), (500, 1000), (1000, 1500), (1500, 2000)],
+}
+
+
+def training_groups(scene):
+    """get_indexes(is_training=True) (train.py:60-65,75-141): for every i in a range, the window [i, i+1, i+2, i+3] AND its
+    time reversal [i+3, i+2, i+1, i] (the filter is trained in both directions of time)."""
+    if scene not in _TRAIN_RANGES:
+        raise ValueError("Invalid scene: %r" % (scene,))        # reference prints and exit()s (train.py:142-144)
+    groups = []
+    for s, e in _TRAIN_RANGES[scene]:
+        for i in range(s, e - 3):
+            groups.append([i, i + 1, i + 2, i + 3])
+            groups.append([i + 3, i + 2, i + 1, i])
+    return groups
+
+
+def prepare_window(labels_full, transform_inv):
+    """train.py:273-280: nearest-neighbour /8 of labels and masks, mask == 1.0, labels moved into the network's frame with
+    ApplyTransform(gt, transform, inverse=True) where `transform` = get_transform() = inv(transform.txt) -- i.e. gt is
+    multiplied by transform.txt itself.  labels_full: [B,H,W,4] (xyz + mask).  Returns (gt8 [B,h,w,3], mask8 [B,h,w,1]) float32."""
+    lab8 = np.asarray(labels_full, np.float32)[:, ::8, ::8]
+    T = np.linalg.inv(np.asarray(transform_inv, np.float64))
+    gt = lab8[..., :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+    mask = (lab8[..., 3:4] == 1.0).astype(np.float32)
+    return np.ascontiguousarray(gt.astype(np.float32)), np.ascontiguousarray(mask)
+
+
+class Trainer:
+    """`run` + `solver` of train.py on one Engine.  step() returns the scalars the reference prints every DISPLAY steps."""
+
+    def __init__(self, weights, spec=None, train_scoordnet=True, fix_flownet=False, base_lr=BASE_LR, weight_decay=WEIGHT_DECAY,
+                 stepvalue=None, gamma=GAMMA, device=None, engine=None):
+        from .engine import Engine
+        self.spec = spec or KFNetDataSpec()
+        self.engine = engine or Engine(weights, mode="fp32", image_size=self.spec.image_size, device=device)
+        self.base_lr, self.weight_decay, self.gamma = base_lr, weight_decay, gamma
+        self.stepvalue = stepvalue if stepvalue is not None else STEPVALUE.get(self.spec.scene, 80000)
+        self.engine.train_begin(self.spec.batch_size, train_scoordnet, not fix_flownet)   # train.py:283-285
+        self.global_step = 0
+
+    def step(self, images, gt_coords, masks, apply_update=True):
+        """images: uint8 [B,H,W,3]; gt_coords [B,h,w,3] / masks [B,h,w,1] as prepare_window() returns them (numpy or cuda tensors)."""
+        import torch
+        dev = torch.device("cuda", self.engine.device)
+        to = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dev, dt).contiguous()
+        out = self.engine.train_step(to(images, torch.uint8), to(gt_coords, torch.float32), to(masks, torch.float32), self.base_lr,
+                                     self.weight_decay, self.stepvalue, self.gamma, apply_update)
+        if apply_update:
+            self.global_step += 1
+        return out
+
+    def weights(self):
+        from .synth import weight_shapes
+        return {name: self.engine.train_get(name) for name in weight_shapes()}
+
+    def save(self, model_folder, step=None):
+        """`saver.save(sess, model_folder/model.ckpt, global_step)` (train.py:379-384) as this package's .npz container."""
+        from . import synth
+        path = os.path.join(model_folder, "model.ckpt-%d.npz" % (self.global_step if step is None else step))
+        synth.save_weights(path, self.weights())
+        return path
+
+
+def train(image_list, label_list, transform_file, snapshot=None, scene="stairs", model_folder="", max_steps=None, fix_flownet=False,
+          weights=None, display=DISPLAY, snapshot_every=SNAPSHOT, device=None, quiet=False):
+    """The loop of train.py:347-420 over the scene's training windows, in order (the reference shuffles its queue with a
+    fixed seed; order only matters for reproducing a particular run)."""
+    from .eval import get_transform, load_image, load_label, load_snapshot_weights, read_lines
+    image_paths, label_paths = read_lines(image_list), read_lines(label_list)
+    assert len(image_paths) == len(label_paths)
+    spec = KFNetDataSpec(scene=scene)
+    groups = [g for g in training_groups(scene) if max(g) < len(image_paths)]
+    if not groups:
+        raise ValueError("no training window fits the image list")
+    Tinv = get_transform(transform_file)
+    tr = Trainer(weights if weights is not None else load_snapshot_weights(snapshot), spec, fix_flownet=fix_flownet, device=device)
+    n = max_steps if max_steps is not None else len(groups)
+    hist = []
+    for it in range(n):
+        g = groups[it % len(groups)]
+        images = np.stack([load_image(image_paths[f]) for f in g])
+        labels = np.stack([load_label(label_paths[f], spec.image_size) for f in g])
+        gt8, mask8 = prepare_window(labels, Tinv)
+        out = tr.step(images, gt8, mask8)
+        hist.append(out)
+        if not quiet and (it % display == 0):
+            print("step %d, lr = %.6g, loss = %.4f, m_loss = %.4f, t_loss = %.4f, kf_loss = %.4f, m_acc = %.3f, t_acc = %.3f, kf_acc = %.3f, "
+                  "reg = %.4f" % (tr.global_step, out["lr"], out["loss"], out["measure_loss"], out["temporal_loss"], out["kf_loss"],
+                                  out["measure_accuracy"], out["temporal_accuracy"], out["kf_accuracy"], out["reg_loss"]))
+        if model_folder and os.path.isdir(model_folder) and (tr.global_step % snapshot_every == 0 or it + 1 == n):
+            tr.save(model_folder)
+    return tr, hist
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--input_folder", default="")
+    ap.add_argument("--model_folder", default="")
+    ap.add_argument("--scene", default="")
+    ap.add_argument("--max_steps", type=int, default=None)
+    ap.add_argument("--fix_flownet", action="store_true")
+    ap.add_argument("--gpu", type=int, default=0)
+    a = ap.parse_args(argv)
+    from .eval import get_snapshot
+    snapshot, _ = get_snapshot(a.model_folder)
+    train(os.path.join(a.input_folder, "image_list.txt"), os.path.join(a.input_folder, "label_list.txt"),
+          os.path.join(a.input_folder, "transform.txt"), snapshot, scene=a.scene, model_folder=a.model_folder, max_steps=a.max_steps,
+          fix_flownet=a.fix_flownet, device=a.gpu)
+
+
+if __name__ == "__main__":
+    main()

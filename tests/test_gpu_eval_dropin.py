@@ -51,6 +51,23 @@ def test_eval_cli_matches_oracle_on_files(tmp_path, weights, capsys):
         assert err < 1e-4, (t, err)
         np.testing.assert_allclose(np.log(got[..., 3]), np.log(want[..., 3]), atol=1e-4)
     assert len(dists[0]) == T and all(np.isfinite(dists[2]))
+    # the printed per-frame scalars (eval.py:113-118): losses / accuracies score the ONE estimated frame against BOTH labels
+    # of the iteration's batch-of-2 (KFNet.py:214 broadcast), distances against the estimated frame's own label
+    import re
+    rows = [l for l in printed.splitlines() if re.match(r"^\d+, frame ", l)]
+    assert len(rows) == T
+    for t, line in enumerate(rows):
+        vals = dict(re.findall(r"(\w+) = (-?[\d.]+|nan)", line))
+        prev = 1 if t == 0 else t - 1
+        assert line.startswith(f"{t}, frame {prev}~{t},")
+        lab2 = labels[[prev, t]]
+        for tag, c, u in (("m", ref[t].measure_coord, ref[t].measure_unc), ("t", ref[t].temp_coord, ref[t].temp_unc),
+                          ("kf", ref[t].kf_coord, ref[t].kf_unc)):
+            l_ref, a_ref = O.coord_loss_with_uncertainty(c.numpy(), u.numpy(), lab2[..., :3], lab2[..., 3:4], Tm)
+            assert abs(float(vals["l_" + tag]) - l_ref) < 2e-3, (t, tag, vals, l_ref)
+            assert abs(float(vals["a_" + tag]) - a_ref) < 2e-3, (t, tag, vals, a_ref)
+        d_ref, _ = O.dist_error(ref[t].out_map.numpy()[..., :3], labels[t][::8, ::8, :3], labels[t][::8, ::8, 3:4])
+        assert abs(float(vals["d_kf"]) - d_ref) < 2e-3 * max(1.0, abs(d_ref)), (t, vals["d_kf"], d_ref)
 
 
 def test_kf_fusion_16_tuple(tmp_path, weights):

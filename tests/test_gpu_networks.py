@@ -1,16 +1,20 @@
 """GPU parity of the network stages and the whole eval path vs the CPU oracle and the committed golden
-vectors (reference source on the TF1 shim).  fp32 mode: 1e-4 on coordinate maps and log-sigma (north_star
-tolerance); bf16 mode: error vs the fp64 oracle reported next to a documented looser bound."""
+vectors (reference source on the TF1 shim).  fp32 / bf16x3 / fp16x2 modes: 1e-4 on coordinate maps and log-sigma
+(north_star tolerance).  bf16 mode: no free-hand bound -- the kernels are compared with the bf16-STORAGE MODEL of the
+fp64 oracle (oracle/kfnet_quant_oracle.py: same weights / activations rounded to bf16 at the same places) and must agree
+to one bf16 ulp of the output scale; the model's own distance to the exact oracle (the cost of bf16 storage) is printed."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import kfnet_oracle as O
+from oracle import kfnet_quant_oracle as Q
 from tests.golden import cases
 from tests.util import assert_close_rms, gpu_setup, rel_err_quantile, rms_rel_err
 
 pytestmark = pytest.mark.gpu
-BF16_TOL = 0.12      # bf16 activations through 12 (+7+14) layers; measured values are printed by the tests
+BF16_ULP = 2.0 ** -8  # bf16 mode vs the bf16-storage model of the fp64 oracle: one bf16 ulp, rms-relative (kfnet_quant_oracle.py)
+BF16_SANITY = 0.2     # bf16 mode vs the EXACT oracle: printed, and only sanity-checked (measured 2.6e-2 on the seeded weights)
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +35,7 @@ def _u8(x):
     return torch.from_numpy(np.ascontiguousarray(x)).to(torch.uint8).cuda().contiguous()
 
 
-def test_scoordnet_and_tower_small_vs_golden(small, golden):
+def test_scoordnet_and_tower_small_vs_golden(small, golden, weights):
     imgs = cases.small_images(2, seed=5)
     m = small["fp32"].scoordnet(_u8(imgs)).cpu()
     f = small["fp32"].oflow_feat(_u8(imgs)).cpu()
@@ -40,16 +44,34 @@ def test_scoordnet_and_tower_small_vs_golden(small, golden):
     assert_close_rms(f, golden["small_rec_feat"], 1e-4, "tower features")
     mb = small["bf16"].scoordnet(_u8(imgs)).cpu()
     fb = small["bf16"].oflow_feat(_u8(imgs)).cpu()
-    print("bf16 small: coord err", assert_close_rms(mb[1:2, ..., :3], golden["small_rec_measure_coord"], BF16_TOL, "bf16 coord"),
-          "feat err", assert_close_rms(fb, golden["small_rec_feat"], BF16_TOL, "bf16 feat"))
+    cq, uq = Q.scoordnet(imgs.astype(np.float32), weights)
+    fq = Q.oflow_feat(imgs.astype(np.float32), weights)
+    print("bf16 small vs bf16-storage model: coord", assert_close_rms(mb[..., :3], cq, BF16_ULP, "bf16 coord vs storage model"),
+          "log sigma", assert_close_rms(torch.log(mb[..., 3:4]), torch.log(uq), BF16_ULP, "bf16 log sigma vs storage model"),
+          "feat", assert_close_rms(fb, fq, BF16_ULP, "bf16 feat vs storage model"),
+          "| vs exact: coord", assert_close_rms(mb[1:2, ..., :3], golden["small_rec_measure_coord"], BF16_SANITY, "bf16 coord"),
+          "feat", assert_close_rms(fb, golden["small_rec_feat"], BF16_SANITY, "bf16 feat"),
+          "| model vs exact: coord", rms_rel_err(cq[1:2], golden["small_rec_measure_coord"]))
 
 
-def test_recursive_step_full_480x640_vs_golden(full, golden):
+def test_recursive_step_full_480x640_vs_golden(full, golden, weights):
     """One GetKFCoordRecursive step at full size: every fetched tensor of eval.py:78-83 vs the golden fixture."""
     from kfnet_b200 import KFNet, KFNetDataSpec
     imgs = cases.full_images()
     lc, lu = (torch.tensor(s, dtype=torch.float32).cuda() for s in cases.full_state())
-    for mode, tol in (("fp32", 1e-4), ("bf16x3", 1e-4), ("fp16x2", 1e-4), ("bf16", BF16_TOL)):
+    # bf16 mode is checked against the bf16-storage model of the same step (fp64 arithmetic, bf16 storage)
+    imf = imgs.astype(np.float32)
+    q_c, q_u = Q.scoordnet(imf[1:2], weights)
+    q_f = Q.oflow_feat(imf, weights)
+    with Q._patched_oflownet():
+        q_tc, q_tu = O.build_oflownet(q_f[0:1], q_f[1:2], lc.cpu().double(), lu.cpu().double(), weights, torch.float64)
+    q_kc, q_ku = O.build_kf_coord(q_tc, q_tu, q_c, q_u)
+    qref = dict(full_rec_feat=q_f, full_rec_measure_coord=q_c, full_rec_measure_unc=q_u, full_rec_temp_coord=q_tc,
+                full_rec_temp_unc=q_tu, full_rec_kf_coord=q_kc, full_rec_kf_unc=q_ku)
+    for mode, tol in (("fp32", 1e-4), ("bf16x3", 1e-4), ("fp16x2", 1e-4), ("bf16", BF16_ULP)):
+        exact = golden
+        if mode == "bf16":
+            golden = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in qref.items()}
         net = KFNet(_u8(imgs), KFNetDataSpec(batch_size=2), engine=full[mode])
         mc, mu = net.GetMeasureCoord2()
         tc, tu, kc, ku = net.GetKFCoordRecursive(lc, lu)
@@ -71,8 +93,11 @@ def test_recursive_step_full_480x640_vs_golden(full, golden):
                      kf_coord=rel_err_quantile(kc, golden["full_rec_kf_coord"], 0.99),
                      log_temp_unc=rel_err_quantile(torch.log(tu), np.log(golden["full_rec_temp_unc"]), 0.99),
                      log_kf_unc=rel_err_quantile(torch.log(ku), np.log(golden["full_rec_kf_unc"]), 0.99))
-            print("bf16 p99", {k: f"{v:.2e}" for k, v in q.items()})
+            print("bf16 vs storage model, warped maps p99", {k: f"{v:.2e}" for k, v in q.items()},
+                  "| bf16 vs exact: measure_coord", f"{rms_rel_err(mc, exact['full_rec_measure_coord']):.2e}",
+                  "feat", f"{rms_rel_err(net.temp_feat_maps, exact['full_rec_feat']):.2e}")
             errs.update(q)
+            golden = exact
         for k, v in errs.items():
             assert v <= tol, f"{mode} {k}: {v:.3e} > {tol}"
         if mode != "bf16":
@@ -103,8 +128,11 @@ def test_eval_sequences_small_vs_oracle(small, weights):
     e = assert_close_rms(out[..., :3], ref[..., :3], 1e-4, "eval out coords")
     e2 = assert_close_rms(torch.log(out[..., 3]), torch.log(ref[..., 3]), 1e-4, "eval out log confidence")
     outb = small["bf16"].eval_sequences(dev, Tm, reinit_period=4, frames_per_batch=4, pairs_per_batch=2).cpu()
-    eb = rel_err_quantile(outb[..., :3], ref[..., :3], 0.99)
-    assert eb <= BF16_TOL, f"bf16 eval out coords p99 {eb}"
+    refq = torch.stack([torch.stack([r.out_map for r in Q.eval_sequence(q_, weights, Tm, seq_len=4)]) for q_ in seqs]).float()
+    eb = rel_err_quantile(outb[..., :3], refq[..., :3], 0.99)
+    assert eb <= BF16_ULP, f"bf16 eval out coords vs the bf16-storage model, p99 {eb}"
+    print(f"bf16 eval vs storage model: p99 {eb:.2e}, max {rms_rel_err(outb[..., :3], refq[..., :3]):.2e}; vs exact p99 "
+          f"{rel_err_quantile(outb[..., :3], ref[..., :3], 0.99):.2e}")
     outx = small["bf16x3"].eval_sequences(dev, Tm, reinit_period=4, frames_per_batch=4, pairs_per_batch=5).cpu()
     ex = assert_close_rms(outx[..., :3], ref[..., :3], 1e-4, "bf16x3 (error-compensated tensor-core) eval out coords")
     assert_close_rms(torch.log(outx[..., 3]), torch.log(ref[..., 3]), 1e-4, "bf16x3 eval out log confidence")
@@ -132,7 +160,11 @@ def test_scoordnet_batch8_full_vs_oracle(full, weights):
         e_or = rms_rel_err(c32, c64)
         e32 = assert_close_rms(m32[t:t + 1, ..., :3], c64, 1e-4, "fp32 mode coord")
         assert_close_rms(torch.log(m32[t:t + 1, ..., 3:4]), torch.log(u64), 1e-4, "fp32 mode log sigma")
-        ebf = assert_close_rms(mbf[t:t + 1, ..., :3], c64, BF16_TOL, "bf16 mode coord")
+        cq, uq = Q.scoordnet(imgs[t:t + 1].astype(np.float32), weights)
+        ebq = assert_close_rms(mbf[t:t + 1, ..., :3], cq, BF16_ULP, "bf16 mode coord vs the bf16-storage model")
+        assert_close_rms(torch.log(mbf[t:t + 1, ..., 3:4]), torch.log(uq), BF16_ULP, "bf16 mode log sigma vs the bf16-storage model")
+        ebf = assert_close_rms(mbf[t:t + 1, ..., :3], c64, BF16_SANITY, "bf16 mode coord vs exact")
+        print(f"frame {t}: bf16 mode vs bf16-storage model {ebq:.2e}; model vs exact {rms_rel_err(cq, c64):.2e}")
         ex3 = assert_close_rms(mx3[t:t + 1, ..., :3], c64, 1e-4, "bf16x3 mode coord (tcgen05, error-compensated)")
         assert_close_rms(torch.log(mx3[t:t + 1, ..., 3:4]), torch.log(u64), 1e-4, "bf16x3 mode log sigma")
         eh2 = assert_close_rms(mh2[t:t + 1, ..., :3], c64, 1e-4, "fp16x2 mode coord (tcgen05, two fp16 limbs)")

@@ -1,0 +1,166 @@
+"""GPU parity of the training path (csrc/train.cu) against the training oracle (oracle/kfnet_train_oracle.py:
+torch autograd in fp64 through the inference oracle): loss scalars, the gradient of EVERY variable, Adam updates over two
+consecutive steps, frozen scopes, the KFNet(train_scoordnet=..., train_oflownet=...) surface, and commit -> inference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kfnet_oracle as O
+from oracle import kfnet_train_oracle as TO
+from tests.golden import cases
+from tests.util import gpu_setup, rms_rel_err
+
+pytestmark = pytest.mark.gpu
+WD, LR, DECAY, GAMMA = 1e-4, 1e-4, 80000, 0.5
+GRAD_TOL = 2e-4        # fp32 backward through up to 12 + 14 layers vs fp64 autograd, rms-relative per variable
+
+
+def _case():
+    g = np.load(os.path.join(os.path.dirname(cases.__file__), "kfnet_reference_training_on_shim.npz"))
+    tc = cases.training_case()
+    return tc["images"], g["gt_network_frame"].astype(np.float64), (tc["mask"] == 1.0).astype(np.float64)
+
+
+def _dev(imgs, gt, mask):
+    return (torch.from_numpy(np.ascontiguousarray(imgs)).to(torch.uint8).cuda(), torch.from_numpy(gt).float().cuda().contiguous(),
+            torch.from_numpy(mask).float().cuda().contiguous())
+
+
+@pytest.fixture(scope="module")
+def oracle_two_steps(weights):
+    imgs, gt, mask = _case()
+    state = {}
+    w1, scal1, grads1 = TO.train_step(weights, imgs, gt, mask, state, LR, WD, DECAY, GAMMA)
+    w2, scal2, grads2 = TO.train_step({k: v.numpy() for k, v in w1.items()}, imgs, gt, mask, state, LR, WD, DECAY, GAMMA)
+    return dict(w1=w1, scal1=scal1, grads1=grads1, w2=w2, scal2=scal2, grads2=grads2)
+
+
+def test_losses_gradients_and_two_adam_steps_match_the_oracle(weights, oracle_two_steps):
+    gpu_setup()
+    from kfnet_b200.engine import Engine
+    imgs, gt, mask = _case()
+    d_imgs, d_gt, d_mask = _dev(imgs, gt, mask)
+    eng = Engine(weights, mode="fp32", image_size=cases.SMALL_HW)
+    eng.train_begin(4)
+    o = oracle_two_steps
+    # forward only: scalars of train.py `run`
+    s0 = eng.train_step(d_imgs, d_gt, d_mask, LR, WD, DECAY, GAMMA, apply_update=False)
+    for k in ("loss", "measure_loss", "temporal_loss", "kf_loss"):
+        assert abs(s0[k] - o["scal1"][k]) <= 1e-4 * max(1.0, abs(o["scal1"][k])), (k, s0[k], o["scal1"][k])
+    for k in ("measure_accuracy", "temporal_accuracy", "kf_accuracy"):
+        assert abs(s0[k] - o["scal1"][k]) <= 1.5 / (4 * 8 * 12), (k, s0[k], o["scal1"][k])     # at most one pixel on the 5 cm threshold
+    reg = float(TO.l2_regularization({k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in weights.items()}, WD))
+    assert abs(s0["reg_loss"] - reg) <= 1e-5 * reg and abs(s0["lr"] - LR) < 1e-12
+    # gradient of every variable (the oracle's gradient includes the regulariser term wd * w; the kernel adds it inside Adam)
+    worst = {}
+    for name in weights:
+        want = o["grads1"][name].numpy() - WD * np.asarray(weights[name], np.float64)
+        got = eng.train_get(name, "grad")
+        worst[name] = rms_rel_err(got, want)
+    bad = {k: v for k, v in worst.items() if not v <= GRAD_TOL}
+    print("gradient errors (rms-relative): max %.2e at %s; median %.2e" % (max(worst.values()), max(worst, key=worst.get),
+                                                                          float(np.median(list(worst.values())))))
+    assert not bad, bad
+    # parameters untouched by a forward/backward-only call
+    np.testing.assert_array_equal(eng.train_get("ScoreNet/conv4b/kernel"), np.asarray(weights["ScoreNet/conv4b/kernel"], np.float32))
+
+    def check_update(prev, new_oracle, tag):
+        # Adam's first steps move every parameter by about lr * sign(g): compare the UPDATES, in units of the learning rate
+        worst_u = 0.0
+        for name in weights:
+            got = eng.train_get(name).astype(np.float64) - np.asarray(prev[name], np.float64)
+            want = new_oracle[name].numpy() - np.asarray(prev[name], np.float64)
+            e = np.abs(got - want).max() / LR
+            worst_u = max(worst_u, e)
+            # fp32 storage of the parameter itself limits the resolvable update: ulp(|p|) / lr
+            ulp = np.spacing(np.abs(np.asarray(prev[name], np.float32)).max()) / LR
+            assert e <= 2e-2 + 2 * ulp, (tag, name, e, ulp)
+        print(f"{tag}: worst parameter-update error = {worst_u:.2e} learning rates")
+
+    s1 = eng.train_step(d_imgs, d_gt, d_mask, LR, WD, DECAY, GAMMA)
+    assert abs(s1["loss"] - o["scal1"]["loss"]) <= 1e-4 * max(1.0, abs(o["scal1"]["loss"]))
+    check_update(weights, o["w1"], "step 1")
+    w1_np = {k: v.numpy() for k, v in o["w1"].items()}
+    s2 = eng.train_step(d_imgs, d_gt, d_mask, LR, WD, DECAY, GAMMA)
+    assert abs(s2["loss"] - o["scal2"]["loss"]) <= 2e-4 * max(1.0, abs(o["scal2"]["loss"])), (s2["loss"], o["scal2"]["loss"])
+    assert abs(s2["lr"] - LR * GAMMA ** (1 / DECAY)) < 1e-10          # exponential_decay at global_step 1
+    check_update(w1_np, o["w2"], "step 2")
+    # Adam moments after two steps
+    for name in ("ScoreNet/conv1a/kernel", "Temporal/conv6/kernel", "Temporal/upconv1/kernel", "Temporal/uncertainty/bias"):
+        m = eng.train_get(name, "m")
+        g1 = o["grads1"][name].numpy(); g2 = o["grads2"][name].numpy()
+        want_m = 0.9 * (0.1 * g1) + 0.1 * g2
+        assert rms_rel_err(m, want_m) <= 5e-3, (name, rms_rel_err(m, want_m))
+    eng.close()
+
+
+def test_frozen_flownet_and_kfnet_loss_surface(weights, oracle_two_steps):
+    gpu_setup()
+    from kfnet_b200 import KFNet, KFNetDataSpec
+    from kfnet_b200.engine import Engine
+    imgs, gt, mask = _case()
+    d_imgs, d_gt, d_mask = _dev(imgs, gt, mask)
+    eng = Engine(weights, mode="fp32", image_size=cases.SMALL_HW)
+    # KFNet(images, spec, train_scoordnet=True, train_oflownet=False): the --fix_flownet configuration (train.py:283-285)
+    net = KFNet(d_imgs, KFNetDataSpec(batch_size=4, image_size=cases.SMALL_HW), True, False, engine=eng)
+    lm, am = net.MeasureCoordLoss(d_gt, d_mask, images=d_imgs)
+    lt, at = net.TemporalCoordLoss(d_gt, d_mask, images=d_imgs)
+    lk, ak = net.KFCoordLoss(d_gt, d_mask, images=d_imgs)
+    o = oracle_two_steps["scal1"]
+    for got, key in ((lm, "measure_loss"), (lt, "temporal_loss"), (lk, "kf_loss")):
+        assert abs(got - o[key]) <= 1e-4 * max(1.0, abs(o[key])), (key, got, o[key])
+    s = eng.train_step(d_imgs, d_gt, d_mask, LR, WD, DECAY, GAMMA)
+    # only ScoreNet variables are regularised and updated
+    reg = float(TO.l2_regularization({k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in weights.items() if k.startswith("ScoreNet/")}, WD))
+    assert abs(s["reg_loss"] - reg) <= 1e-5 * reg
+    np.testing.assert_array_equal(eng.train_get("Temporal/conv0/kernel"), np.asarray(weights["Temporal/conv0/kernel"], np.float32))
+    np.testing.assert_array_equal(eng.train_get("Temporal/feat1/bias"), np.asarray(weights["Temporal/feat1/bias"], np.float32))
+    assert np.abs(eng.train_get("ScoreNet/conv7/kernel") - np.asarray(weights["ScoreNet/conv7/kernel"], np.float32)).max() > 0
+    eng.close()
+
+
+def test_training_reduces_the_loss_and_commit_feeds_inference(weights):
+    """A few steps on one fixed window must lower the loss; kfn_train_commit makes the inference entry points run the trained
+    parameters (checked against the oracle's forward on the fetched weights)."""
+    gpu_setup()
+    from kfnet_b200.train import Trainer
+    from kfnet_b200 import KFNetDataSpec
+    imgs, gt, mask = _case()
+    tr = Trainer(weights, KFNetDataSpec(batch_size=4, image_size=cases.SMALL_HW), base_lr=1e-4)
+    losses = [tr.step(imgs, gt.astype(np.float32), mask.astype(np.float32))["loss"] for _ in range(8)]
+    print("training losses:", ["%.4f" % v for v in losses])
+    assert losses[-1] < losses[0] and all(np.isfinite(losses))
+    assert tr.global_step == 8
+    tr.engine.train_commit()
+    new_w = tr.weights()
+    got = tr.engine.scoordnet(torch.from_numpy(np.ascontiguousarray(imgs)).to(torch.uint8).cuda()).cpu()
+    c64, u64 = O.scoordnet(imgs.astype(np.float32), new_w, torch.float64)
+    assert rms_rel_err(got[..., :3], c64) <= 1e-4 and rms_rel_err(torch.log(got[..., 3:4]), torch.log(u64)) <= 1e-4
+    assert rms_rel_err(got[..., :3], O.scoordnet(imgs.astype(np.float32), weights, torch.float64)[0]) > 1e-4   # it did change
+
+
+def test_one_full_resolution_step_runs(weights):
+    """480x640, window of 4: the shapes the reference trains on (finite scalars, every gradient finite and non-trivial)."""
+    gpu_setup()
+    from kfnet_b200 import synth
+    from kfnet_b200.engine import Engine
+    eng = Engine(weights, mode="fp32", image_size=(480, 640))
+    eng.train_begin(4)
+    imgs = torch.from_numpy(synth.make_sequence(4, seed=3)).cuda()
+    pred = eng.scoordnet(imgs)
+    rng = np.random.default_rng(0)
+    gt = (pred[..., :3].cpu().numpy() + rng.normal(size=(4, 60, 80, 3)) * 0.004).astype(np.float32)
+    mask = (rng.uniform(size=(4, 60, 80, 1)) > 0.2).astype(np.float32)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s = eng.train_step(imgs, torch.from_numpy(gt).cuda(), torch.from_numpy(mask).cuda())       # warm (allocations)
+    ev0.record()
+    s = eng.train_step(imgs, torch.from_numpy(gt).cuda(), torch.from_numpy(mask).cuda())
+    ev1.record(); torch.cuda.synchronize()
+    print("full-resolution training step: %.1f ms; scalars %s" % (ev0.elapsed_time(ev1), {k: round(v, 4) for k, v in s.items()}))
+    assert all(np.isfinite(list(s.values())))
+    for name in ("ScoreNet/conv1a/kernel", "ScoreNet/conv4b/kernel", "Temporal/feat1/kernel", "Temporal/upconv0/kernel", "Temporal/fc1/kernel"):
+        g = eng.train_get(name, "grad")
+        assert np.isfinite(g).all() and np.abs(g).max() > 0, name
+    eng.close()
