@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges are no-ops unless a profiler attached its injection library
+
 #include "../../include/kfnet_b200.h"
 
 namespace kfn {
@@ -41,6 +43,14 @@ extern thread_local int64_t* g_handle_launches;   // counter of the handle whose
       return KFN_ERR_ARG;                                                                          \
     }                                                                                              \
   } while (0)
+
+// NVTX range over a stage of the path (shows up in Nsight Systems / ncu --nvtx): scoped push/pop
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Handle-less entry points run on the device that owns their buffers (not on whatever device happens to be current):
 // makes `dev` the current device and returns it through *dev.  SM counts are cached per device.

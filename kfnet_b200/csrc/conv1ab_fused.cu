@@ -233,16 +233,16 @@ conv1ab_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 b = __ldg(b4 + g);
-          v[4 * g + 0] = fmaxf(__uint_as_float(rr[4 * g + 0]) + b.x, 0.f);
-          v[4 * g + 1] = fmaxf(__uint_as_float(rr[4 * g + 1]) + b.y, 0.f);
-          v[4 * g + 2] = fmaxf(__uint_as_float(rr[4 * g + 2]) + b.z, 0.f);
-          v[4 * g + 3] = fmaxf(__uint_as_float(rr[4 * g + 3]) + b.w, 0.f);
+          v[4 * g + 0] = __uint_as_float(rr[4 * g + 0]) + b.x;      // the ReLU rides on the bf16 conversion (F2FP.RELU)
+          v[4 * g + 1] = __uint_as_float(rr[4 * g + 1]) + b.y;
+          v[4 * g + 2] = __uint_as_float(rr[4 * g + 2]) + b.z;
+          v[4 * g + 3] = __uint_as_float(rr[4 * g + 3]) + b.w;
         }
         if (rvalid) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            uint4 o = make_uint4(pack_bf16(v[8 * g + 0], v[8 * g + 1]), pack_bf16(v[8 * g + 2], v[8 * g + 3]),
-                                 pack_bf16(v[8 * g + 4], v[8 * g + 5]), pack_bf16(v[8 * g + 6], v[8 * g + 7]));
+            uint4 o = make_uint4(pack_bf16_relu(v[8 * g + 0], v[8 * g + 1]), pack_bf16_relu(v[8 * g + 2], v[8 * g + 3]),
+                                 pack_bf16_relu(v[8 * g + 4], v[8 * g + 5]), pack_bf16_relu(v[8 * g + 6], v[8 * g + 7]));
             if (!inside) o = make_uint4(0u, 0u, 0u, 0u);   // zero padding of conv1b's input (tf.layers.conv2d SAME)
             *reinterpret_cast<uint4*>(dst + (((blk * 4 + g) ^ sw7) << 4)) = o;
           }
@@ -297,16 +297,16 @@ conv1ab_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 b = __ldg(b4 + g);
-          v[4 * g + 0] = fmaxf(__uint_as_float(rr[4 * g + 0]) + b.x, 0.f);
-          v[4 * g + 1] = fmaxf(__uint_as_float(rr[4 * g + 1]) + b.y, 0.f);
-          v[4 * g + 2] = fmaxf(__uint_as_float(rr[4 * g + 2]) + b.z, 0.f);
-          v[4 * g + 3] = fmaxf(__uint_as_float(rr[4 * g + 3]) + b.w, 0.f);
+          v[4 * g + 0] = __uint_as_float(rr[4 * g + 0]) + b.x;      // the ReLU rides on the bf16 conversion (F2FP.RELU)
+          v[4 * g + 1] = __uint_as_float(rr[4 * g + 1]) + b.y;
+          v[4 * g + 2] = __uint_as_float(rr[4 * g + 2]) + b.z;
+          v[4 * g + 3] = __uint_as_float(rr[4 * g + 3]) + b.w;
         }
         uint4* o = reinterpret_cast<uint4*>(orow + blk * 64);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          o[g] = make_uint4(pack_bf16(v[8 * g + 0], v[8 * g + 1]), pack_bf16(v[8 * g + 2], v[8 * g + 3]),
-                            pack_bf16(v[8 * g + 4], v[8 * g + 5]), pack_bf16(v[8 * g + 6], v[8 * g + 7]));
+          o[g] = make_uint4(pack_bf16_relu(v[8 * g + 0], v[8 * g + 1]), pack_bf16_relu(v[8 * g + 2], v[8 * g + 3]),
+                            pack_bf16_relu(v[8 * g + 4], v[8 * g + 5]), pack_bf16_relu(v[8 * g + 6], v[8 * g + 7]));
       }
       tc_fence_before();
       __syncwarp();

@@ -76,6 +76,10 @@ struct __align__(8) TcParams {
   void* out2;
   int x3acc;                    // 1: four 128-column TMEM accumulators (3 main-term splits + corrections), single-buffered
   int la[6], lw[6];
+  // halo mode with limbs (bf16x3 / fp16x2): the haloed block is loaded once per (A limb, channel chunk) and every tap x
+  // every W limb that pairs with that A limb is a shifted-descriptor MMA on the resident weights
+  int a_chunks, w_chunks, n_limbs_a, n_limbs_w;
+  uint32_t term_mask[3];        // bit lw of term_mask[la]: the product (A limb la) x (W limb lw) is accumulated
   int f16;                      // limbs are fp16 (KFN_MODE_FP16X2): limb 1 holds the residual scaled by 2^11
   float corr_scale;             // factor applied to the correction accumulator in the epilogue (1, or 2^-11 for fp16 limbs)
   uint32_t epi_stage_off;       // byte offset (from the 1024-aligned smem base) of the epilogue staging area
@@ -252,6 +256,49 @@ __device__ __forceinline__ void mma_role_x3(const TcParams& p, uint32_t smem_bas
           adesc += stage16;
           if (++s == p.stages) { s = 0; ph ^= 1u; adesc = a0; }
         }
+      }
+    }
+    umma_commit(smem_u32(&s_tfull[0]));
+  }
+}
+
+// halo mode + limbs: accumulator assignment as mma_role_x3 (main term round-robin by tap over accumulators 0..2, every
+// correction term into accumulator 3), operand walk as mma_role_halo
+template <int KSTEPS>
+__device__ __forceinline__ void mma_role_halo_x3(const TcParams& p, uint32_t smem_base, uint32_t tmem_base, int total_tiles,
+                                                 uint64_t* s_full, uint64_t* s_empty, uint64_t* s_tfull, uint64_t* s_tempty,
+                                                 uint64_t* s_wbar) {
+  mbar_wait(smem_u32(s_wbar), 0);
+  const uint64_t a_fixed = ((uint64_t)p.desc_hi_halo << 32) | (1ull << 16);
+  const uint64_t b_fixed = ((uint64_t)p.desc_hi << 32) | (1ull << 16);
+  const uint64_t stage16 = (uint64_t)(p.stage_bytes >> 4);
+  const uint64_t a0 = a_fixed | (uint64_t)((smem_base + p.w_bytes_total) >> 4);
+  const uint64_t b0 = b_fixed | (uint64_t)(smem_base >> 4);
+  const uint64_t wtile16 = (uint64_t)(p.w_tile_bytes >> 4);
+  int s = 0, j = 0;
+  uint32_t ph = 0;
+  uint64_t adesc = a0;
+  TileIter it;
+  for (it.init(p, total_tiles); it.valid(); it.next(p), ++j) {
+    mbar_wait(smem_u32(&s_tempty[0]), ((uint32_t)j & 1u) ^ 1u);
+    tc_fence_after();
+    uint32_t used = 0;
+    for (int la = 0; la < p.n_limbs_a; ++la) {
+      for (int kc = 0; kc < p.cpk; ++kc) {
+        mbar_wait(smem_u32(&s_full[s]), ph);
+        tc_fence_after();
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int lw = 0; lw < p.n_limbs_w; ++lw) {
+            if (!((p.term_mask[la] >> lw) & 1u)) continue;
+            const int acc = (la == 0 && lw == 0) ? (tap % 3) : 3;
+            const uint64_t bdesc = b0 + wtile16 * (uint64_t)((tap * p.n_limbs_w + lw) * p.cpk + kc);
+            umma_kblock<KSTEPS>(tmem_base + (uint32_t)acc * p.acc_stride, adesc + (uint64_t)p.tap_off16[tap], bdesc, p.idesc, (used >> acc) & 1u);
+            used |= 1u << acc;
+          }
+        }
+        umma_commit(smem_u32(&s_empty[s]));
+        adesc += stage16;
+        if (++s == p.stages) { s = 0; ph ^= 1u; adesc = a0; }
       }
     }
     umma_commit(smem_u32(&s_tfull[0]));
@@ -453,10 +500,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
     if (producer_lane && p.halo) {
       // resident weights: every (tap, chunk) tile once, one barrier
       const uint32_t wbar = smem_u32(&s_wbar);
-      mbar_expect_tx(wbar, (uint32_t)(p.ntaps * p.kchunks) * p.b_bytes);
+      mbar_expect_tx(wbar, (uint32_t)(p.ntaps * p.w_chunks) * p.b_bytes);
       for (int tap = 0; tap < p.ntaps; ++tap)
-        for (int kc = 0; kc < p.kchunks; ++kc)
-          tma_load_3d(smem_base + (uint32_t)(tap * p.kchunks + kc) * p.w_tile_bytes, &tmB, wbar, kc * p.KC, 0, tap);
+        for (int wc = 0; wc < p.w_chunks; ++wc)     // wc = lw * cpk + kc; channel coordinate lw * w_cin + kc * KC
+          tma_load_3d(smem_base + (uint32_t)(tap * p.w_chunks + wc) * p.w_tile_bytes, &tmB, wbar,
+                      (wc / p.cpk) * p.w_cin + (wc % p.cpk) * p.KC, 0, tap);
       const uint32_t stage0 = smem_base + p.w_bytes_total;
       int s = 0;
       uint32_t ph = 0;
@@ -472,11 +520,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
             tma_prefetch_5d(&tmA, kc * p.KC, (pf.tw << 3) - 1, pf.tn << p.lbn, (pf.th << p.lbh) - 1, 0);
           pf.next(p);
         }
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int ac = 0; ac < p.a_chunks; ++ac) {     // ac = la * cpk + kc; channel coordinate la * in_ls + kc * KC
           mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);
           const uint32_t full = smem_u32(&s_full[s]);
           mbar_expect_tx(full, p.a_bytes);
-          tma_load_5d(stage0 + (uint32_t)s * p.stage_bytes, &tmA, full, kc * p.KC, w0 - 1, n0, h0 - 1, 0);
+          tma_load_5d(stage0 + (uint32_t)s * p.stage_bytes, &tmA, full, (ac / p.cpk) * p.in_ls + (ac % p.cpk) * p.KC, w0 - 1, n0, h0 - 1, 0);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -525,6 +573,10 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
       const int ksteps = p.KC >> 4;
       if (f_im2col) {
         mma_role_im2col<2>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
+      } else if (f_x3acc && p.halo) {
+        if (ksteps == 4) mma_role_halo_x3<4>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
+        else if (ksteps == 2) mma_role_halo_x3<2>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
+        else mma_role_halo_x3<1>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
       } else if (f_x3acc) {
         if (ksteps == 4) mma_role_x3<4>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty);
         else if (ksteps == 2) mma_role_x3<2>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty);
@@ -663,17 +715,28 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
               const float4 bq = __ldg(b4 + q);
               v[4 * q + 0] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
             }
-            if (p.relu) {
+            // single-limb bf16 outputs: the ReLU rides on the conversion (F2FP.RELU)
+            const bool relu_cvt = p.relu && f_out_limbs == 1 && !f_f16;
+            if (p.relu && !relu_cvt) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
             for (int l = 0; l < f_out_limbs; ++l) {
               // stage: row = lane (64 B), 16-byte chunk q at slot q ^ ((lane >> 1) & 3): conflict-free both ways
+              if (relu_cvt) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint32_t w0 = pack_limb(v[8 * q + 0], v[8 * q + 1], f_f16), w1 = pack_limb(v[8 * q + 2], v[8 * q + 3], f_f16);
-                const uint32_t w2 = pack_limb(v[8 * q + 4], v[8 * q + 5], f_f16), w3 = pack_limb(v[8 * q + 6], v[8 * q + 7], f_f16);
-                *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw_st) << 4)) = make_uint4(w0, w1, w2, w3);
+                for (int q = 0; q < 4; ++q) {
+                  const uint32_t w0 = pack_bf16_relu(v[8 * q + 0], v[8 * q + 1]), w1 = pack_bf16_relu(v[8 * q + 2], v[8 * q + 3]);
+                  const uint32_t w2 = pack_bf16_relu(v[8 * q + 4], v[8 * q + 5]), w3 = pack_bf16_relu(v[8 * q + 6], v[8 * q + 7]);
+                  *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw_st) << 4)) = make_uint4(w0, w1, w2, w3);
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint32_t w0 = pack_limb(v[8 * q + 0], v[8 * q + 1], f_f16), w1 = pack_limb(v[8 * q + 2], v[8 * q + 3], f_f16);
+                  const uint32_t w2 = pack_limb(v[8 * q + 4], v[8 * q + 5], f_f16), w3 = pack_limb(v[8 * q + 6], v[8 * q + 7], f_f16);
+                  *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw_st) << 4)) = make_uint4(w0, w1, w2, w3);
+                }
               }
               __syncwarp();
 #pragma unroll
@@ -896,7 +959,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   const cuuint64_t cs = (cuuint64_t)g.in_cs * 2;      // bytes per pixel
 
   // ---- halo mode eligibility: stride-1 3x3, 8-wide tiles, one N tile, weights resident in smem
-  bool halo = tc_halo_enabled() && g.istride == 1 && g.omul == 1 && g.ntaps >= 2 && CoutP <= 256 && g.MW % 8 == 0 &&
+  bool halo = tc_halo_enabled() && g.istride == 1 && g.omul == 1 && g.ntaps >= 2 && CoutP <= bn_cap && g.MW % 8 == 0 &&
               g.IH == g.MH && g.IW == g.MW && g.epi != EPI_L2NORM;
   for (int t = 0; t < g.ntaps; ++t) halo = halo && g.dy[t] >= -1 && g.dy[t] <= 1 && g.dx[t] >= -1 && g.dx[t] <= 1;
   int hbh = 0, hbn = 0;
@@ -906,8 +969,11 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     else halo = false;
   }
   const uint32_t w_tile_bytes = ((uint32_t)(BN * row_bytes) + 1023u) & ~1023u;
-  const uint32_t w_total = (uint32_t)(g.ntaps * (g.Cin / KC)) * w_tile_bytes;
-  if (halo && w_total > 100 * 1024) halo = false;   // (two-CTA plans re-check against their smaller budget below)
+  const int lw_n = g.limbs_w > 1 ? g.limbs_w : 1;
+  const uint32_t w_total = (uint32_t)(g.ntaps * (g.Cin / KC) * lw_n) * w_tile_bytes;   // every (tap, W limb, chunk) tile resident
+  if (halo && w_total > (x3 ? 150u : 100u) * 1024u) halo = false;   // (two-CTA plans re-check against their smaller budget below)
+  static const bool halo_x3_on = env_flag("KFN_TC_HALO_X3", true);   // A/B switch: halo tiles for the limb modes
+  if (x3 && !halo_x3_on) halo = false;
 
   p.N = g.N; p.MH = g.MH; p.MW = g.MW;
   p.istride = g.istride; p.in_cs = g.in_cs;
@@ -929,7 +995,9 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   p.w_cin = g.Cin;
   p.out_limbs = g.limbs_out > 1 ? g.limbs_out : 1;
   p.out_ls = p.out_limbs > 1 ? g.out_ls : 0;
-  if (p.n_terms > 1) halo = false;
+  p.n_limbs_a = limbs_a; p.n_limbs_w = limbs_w;
+  p.a_chunks = limbs_a * p.cpk; p.w_chunks = limbs_w * p.cpk;
+  for (int t = 0; t < p.n_terms; ++t) p.term_mask[p.la[t]] |= 1u << p.lw[t];
   p.x3acc = x3 ? 1 : 0;
   p.phase_cout = g.phase_cout;
   p.split_col = out2 ? g.split_col : 0; p.out2_cs = g.out2_cs; p.out2 = out2;
@@ -1024,7 +1092,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
       plan->threads += 192;
     }
     // halo view: dims (c, w, n, h, 1) so that the box lands in smem as [y][n][x] rows
-    dimA[0] = g.Cin; dimA[1] = g.IW; dimA[2] = g.N; dimA[3] = g.IH; dimA[4] = 1;
+    dimA[0] = (cuuint64_t)(limbs_a - 1) * p.in_ls + g.Cin; dimA[1] = g.IW; dimA[2] = g.N; dimA[3] = g.IH; dimA[4] = 1;
     strA[0] = cs; strA[1] = cs * g.IW * g.IH; strA[2] = cs * g.IW; strA[3] = cs * g.IW * g.IH * g.N;
     boxA[0] = (cuuint32_t)KC; boxA[1] = 10; boxA[2] = (cuuint32_t)hbn; boxA[3] = (cuuint32_t)(hbh + 2); boxA[4] = 1;
   } else {

@@ -708,8 +708,10 @@ int eval_sequences_impl(kfn_handle* h, const uint8_t* images, int S, int T, cons
   const int64_t img_bytes = (int64_t)h->H * h->W * 3;
   int rc;
   if (continues) KFN_CUDA_OK(cudaMemcpyAsync(featbuf, ex->carry + P * 4, (size_t)(P * 32 * 4), cudaMemcpyDeviceToDevice, st));
+  NvtxRange nv_all("kfn_eval_sequences");
   // 1. measurement system + feature tower: frame-parallel over all S*T frames
   for (int64_t f0 = 0; f0 < F; f0 += frames_per_batch) {
+    NvtxRange nv("scoordnet+tower batch");
     const int B = (int)((F - f0) < frames_per_batch ? (F - f0) : frames_per_batch);
     if (batch_ready) KFN_CUDA_OK(cudaStreamWaitEvent(st, batch_ready[f0 / frames_per_batch], 0));
     // both networks start from the same preprocessed input (im2col rows / fp32 image): build it once per batch
@@ -733,12 +735,14 @@ int eval_sequences_impl(kfn_handle* h, const uint8_t* images, int S, int T, cons
   //    sequence re-initialises the filter, eval.py:94-101).
   for (int64_t f0 = continues ? 0 : 1; f0 < F; f0 += pairs_per_batch) {
     const int NP = (int)((F - f0) < pairs_per_batch ? (F - f0) : pairs_per_batch);
+    NvtxRange nv("oflownet pair batch");
     Arena a(sub, sub_bytes);
     if ((rc = oflownet_impl(h, featbuf + f0 * P * 32, feat + f0 * P * 32, NP, flow + f0 * P * 2, sigw + f0 * P, nullptr,
                             nullptr, a, st, false)))
       return rc;
   }
   // 3. serial scan: warp + Kalman update, one CTA per sequence
+  NvtxRange nv_scan("warp+kalman scan");
   if ((rc = launch_kalman_scan(measure, flow, sigw, continues ? ex->carry : nullptr, (ex && ex->carry) ? ex->carry : nullptr, transform,
                                S, T, h->GH, h->GW, first_index, period, nis_gate, out_map, ex ? ex->temp : nullptr,
                                ex ? ex->kf : nullptr, ex ? ex->nis : nullptr, nullptr, st)))

@@ -125,6 +125,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// max(x, 0) folded into the conversion: one F2FP.RELU.BF16.F32.PACK_AB instead of two FMNMX + one F2FP (identical results:
+// rounding commutes with the clamp at 0)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 // one stored limb pair: bf16, or fp16 (KFN_MODE_FP16X2)
 __device__ __forceinline__ uint32_t pack_limb(float a, float b, bool f16) {
   if (f16) {

@@ -798,6 +798,7 @@ int kfn_train_step(kfn_handle* h, const uint8_t* images, const float* gt8, const
   Bufs b;
   plan(t, arena, b);
   int rc;
+  NvtxRange nv_step("kfn_train_step");
 #define RUN(x) do { if ((rc = (x))) return rc; } while (0)
   // ---- operands of this step from the current parameters
   for (int li = 0; li < kNumLayers; ++li)

@@ -30,3 +30,7 @@ q b16
 q b32 --frames_per_batch 32 --pairs_per_batch 32
 q b16p32 --pairs_per_batch 32
 q b16b
+# error-compensated modes: halo tiles on/off
+q fp16x2_halo --mode fp16x2 --steps 2
+KFN_TC_HALO_X3=0 q fp16x2_nohalo --mode fp16x2 --steps 2
+q bf16x3_halo --mode bf16x3 --steps 2
