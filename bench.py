@@ -362,7 +362,7 @@ def run_ours(args):
         dist.broadcast(ok, 0)
 
     # per-stage device times on this rank (events on the launching stream), for the roofline of the dominant kernel
-    def stage_ms(fn, reps=3):
+    def stage_ms(fn, reps=10):
         fn(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -501,8 +501,8 @@ def parity_block(args, eng_bf16, weights, Tm, dev_seq, T, H, W):
     def err(e):
         return spread(run(e), ref)["max"]
 
-    # bf16 mode: its distance to the exact oracle, and to the bf16-STORAGE MODEL of the oracle (same roundings at the same
-    # places, oracle/kfnet_quant_oracle.py) -- the second is what the bf16 tests assert (one bf16 ulp on the 99th percentile)
+    # bf16 mode: its distance to the exact oracle beside the distance of the bf16-STORAGE MODEL of the oracle (exact arithmetic,
+    # same roundings at the same places, oracle/kfnet_quant_oracle.py) to the exact oracle -- the yardstick the bf16 tests use
     from oracle import kfnet_quant_oracle as Q
     t0 = time.perf_counter()
     with torch.no_grad():
@@ -512,8 +512,9 @@ def parity_block(args, eng_bf16, weights, Tm, dev_seq, T, H, W):
                                                 "%d full-resolution frames (frame 0 = re-init, %d filtered frames), oracle %.1f s" % (n, n - 1, oracle_s),
              "bf16": {"vs_exact_fp64_oracle": spread(out_bf16, ref), "vs_bf16_storage_model_of_the_oracle": spread(out_bf16, refq),
                       "storage_model_vs_exact": spread(refq, ref),
-                      "note": "bf16 storage has no tolerance in the reference; the tests hold the kernels to the storage model at 2^-8 "
-                              "(p99; single warped pixels may flip at the sampler edge, which is what the max shows); model run %.1f s"
+                      "note": "bf16 storage has no tolerance in the reference; the tests require kernel-vs-exact <= 1.5 x (p99) / 2 x (max) of "
+                              "storage_model_vs_exact, the error of an exact-arithmetic bf16-storage implementation (single warped pixels "
+                              "flip at the sampler edge in both, which is what the max shows); model run %.1f s"
                               % (time.perf_counter() - t0)}}
     for mode in args.parity_modes.split(","):
         e = Engine(weights, mode=mode, image_size=(H, W), device=eng_bf16.device)

@@ -176,12 +176,14 @@ def _frame_metrics(coords, gt, mask):
 
 
 def eval(image_list, label_list, transform_file, snapshot, scene="stairs", output_folder="", NIS=False,  # noqa: A001
-         mode="fp32", chunk=64, weights=None, engine=None, quiet=False, device=None, stats=None):
+         mode="fp32", chunk=32, weights=None, engine=None, quiet=False, device=None, stats=None, show=False):
     """KFNet/eval.py:31-164.  Frames are decoded by a thread pool straight into pinned staging memory one chunk ahead of
     the GPU; each chunk is ONE C-ABI call (kfn_eval_stream_host: H2D streamed batch by batch, SCoordNet + tower + OFlowNet
     frame-parallel, the serial warp+Kalman scan, D2H of the output maps and of the tensors the printed line needs), with
     the filter state and the last feature map carried on the device between chunks.  `stats` (optional dict) receives
-    frames, seconds and frames_per_s of the loop."""
+    frames, seconds and frames_per_s of the loop.  `show` (the reference's --show, eval.py:121,127-160): instead of saving
+    coord_<idx>.npy, the twelve panels the reference plots per frame are written as show_<idx>.npz (and as a PNG figure
+    when matplotlib is importable) -- this box has no display."""
     import time
     import torch
     from concurrent.futures import ThreadPoolExecutor
@@ -239,12 +241,16 @@ def eval(image_list, label_list, transform_file, snapshot, scene="stairs", outpu
     nxt = plan(0) if n_chunks else None
     carry, last_cur, state = None, None, None
     t_start = time.perf_counter()
+    t_dec = t_gpu = t_met = 0.0            # where the loop's wall time goes: waiting for the decoder, the C-ABI call, host metrics
     for ci in range(n_chunks):
         its, pairs, futs_i, futs_l = nxt
+        t0 = time.perf_counter()
         for f in futs_i:
             f.result()
+        t_dec += time.perf_counter() - t0
         host_imgs = stage[ci & 1][:len(its)]
         nxt = plan(ci + 1) if ci + 1 < n_chunks else None           # decode chunk ci+1 while the GPU runs chunk ci
+        t0 = time.perf_counter()
         if consecutive(its, pairs, last_cur):
             out_t, diag, carry = engine.eval_stream_host(host_imgs, its[0], transform, carry, reinit_period=period, nis_gate=NIS,
                                                          want_diag=True, capacity=chunk)
@@ -252,6 +258,8 @@ def eval(image_list, label_list, transform_file, snapshot, scene="stairs", outpu
             meas_np, temp, kf, nis = (diag[k].numpy() for k in ("measure", "temp", "kf", "nis"))
         else:
             out_map, meas_np, temp, kf, nis, carry = _eval_chunk_general(engine, host_imgs, pairs, its[0], transform, carry, period, NIS)
+        t_gpu += time.perf_counter() - t0
+        t0 = time.perf_counter()
         last_cur = pairs[-1][1]
         lab = {f: fut.result() for f, fut in futs_l.items()}
         gt = np.stack([lab[p[1]][..., :3] for p in pairs])
@@ -277,19 +285,51 @@ def eval(image_list, label_list, transform_file, snapshot, scene="stairs", outpu
                 print("%d, frame %d~%d, l_m = %.3f, l_t = %.3f, l_kf = %.3f, a_m = %.3f, a_t = %.3f, a_kf = %.3f, "
                       "d_m = %.3f, d_t = %.3f, d_kf = %.3f, nis = %.3f"
                       % (i, prev, index, l_m, l_t, l_k, a_m, a_t, a_k, d_m[k], d_t[k], d_kf[k], get_NIS_measurement(nis[k])))
-        if save_dir:                                                                       # eval.py:122-126
+        if show and save_dir:                                                              # eval.py:127-160
+            for k, p in enumerate(pairs):
+                _show_panels(os.path.join(save_dir, "show_" + str(p[1])), mask[k], gt[k], nis[k], meas_np[k], t_meas[k], temp[k], t_temp[k],
+                             kf[k], out_map[k])
+        elif save_dir:                                                                     # eval.py:122-126
             maps = out_map.astype(np.float32, copy=True)
             for k, p in enumerate(pairs):
                 pool.submit(np.save, os.path.join(save_dir, "coord_" + str(p[1]) + ".npy"), maps[k])
+        t_met += time.perf_counter() - t0
+    t0 = time.perf_counter()
     pool.shutdown(wait=True)
+    t_tail = time.perf_counter() - t0
     dt = time.perf_counter() - t_start
     if stats is not None:
-        stats.update(frames=n_iter, seconds=dt, frames_per_s=n_iter / dt if dt > 0 else float("nan"))
+        stats.update(frames=n_iter, seconds=dt, frames_per_s=n_iter / dt if dt > 0 else float("nan"),
+                     wait_decode_s=t_dec, cabi_call_s=t_gpu, host_metrics_s=t_met, drain_saves_s=t_tail)
     if not quiet:
         print("Median dist error: ", *[np.median(d) for d in dists])
         print("Mean dist error: ", *[np.mean(d) for d in dists])
         print("stddev error: ", *[np.std(d) for d in dists])
     return dists
+
+
+def _show_panels(path, mask, gt, nis, meas, t_meas, temp, t_temp, kf, out_map):
+    """The 4 x 3 panel grid of eval.py:131-155 as arrays (+ a PNG when matplotlib is available)."""
+    def dmap(c):
+        return np.minimum(np.sqrt(np.square(c - gt).sum(-1)) * mask[..., 0] * 100.0, 10)
+    panels = {"mask": mask[..., 0], "gt_coords": gt, "nis": np.minimum(nis, 20),
+              "measure_uncertainty": np.minimum(meas[..., 3], 255.0), "measure_coord": t_meas, "measure_dist": dmap(t_meas),
+              "temp_uncertainty": np.minimum(temp[..., 3], 255.0), "temp_coord": t_temp, "temp_dist": dmap(t_temp),
+              "kf_uncertainty": np.minimum(kf[..., 3], 255.0), "kf_coord": out_map[..., :3], "kf_dist": dmap(out_map[..., :3])}
+    np.savez_compressed(path + ".npz", **panels)
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+    except Exception:
+        return
+    fig, _ = plt.subplots(4, 3)
+    for i, (name, a) in enumerate(panels.items()):
+        plt.subplot(4, 3, i + 1)
+        plt.imshow(np.clip(a, 0, 1) if a.ndim == 3 else a)
+        plt.title(name, fontsize=6); plt.axis("off")
+    fig.savefig(path + ".png", dpi=120)
+    plt.close(fig)
 
 
 def _eval_chunk_general(engine, host_imgs, pairs, i0, transform, carry, period, NIS):
@@ -332,15 +372,16 @@ def main(argv=None):
     ap.add_argument("--output_folder", default="")
     ap.add_argument("--scene", default="")
     ap.add_argument("--NIS", action="store_true")
+    ap.add_argument("--show", action="store_true", help="write the reference's 12 diagnostic panels per frame instead of coord_<idx>.npy")
     ap.add_argument("--gpu", type=int, default=0)
     ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16", "bf16x3", "fp16x2"])
-    ap.add_argument("--chunk", type=int, default=64)
+    ap.add_argument("--chunk", type=int, default=32)
     ap.add_argument("--quiet", action="store_true", help="no per-frame line / summary (the output .npy files are unchanged)")
     a = ap.parse_args(argv)
     snapshot, _ = get_snapshot(a.model_folder)
     eval(os.path.join(a.input_folder, "image_list.txt"), os.path.join(a.input_folder, "label_list.txt"),
          os.path.join(a.input_folder, "transform.txt"), snapshot, scene=a.scene, output_folder=a.output_folder,
-         NIS=a.NIS, mode=a.mode, chunk=a.chunk, device=a.gpu, quiet=a.quiet)
+         NIS=a.NIS, mode=a.mode, chunk=a.chunk, device=a.gpu, quiet=a.quiet, show=a.show)
 
 
 if __name__ == "__main__":

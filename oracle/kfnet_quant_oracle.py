@@ -8,12 +8,15 @@ the kernels with THIS model: the fp64 oracle with the same roundings injected at
 
     layer(x) = round_bf16( relu( conv_fp64( x, round_bf16(W) ) + b ) )        (network outputs stay unrounded)
 
-Against it the kernels may only differ by (a) fp32-vs-fp64 accumulation noise (~1e-6 relative) and (b) the rare
-activation that sits so close to a bf16 rounding boundary that (a) flips it by one ulp (2^-8 relative of that one
-activation, then diluted by the following layers' sums).  The expected agreement is therefore a fraction of ONE bf16
-ulp of the output scale; the tests assert 2^-8 = 3.9e-3 (rms-relative max) and print the measured value.
-The error of the model itself against the exact fp64 oracle is the honest "cost of bf16 storage"; bench.py and the
-tests print it beside the kernels' error (they coincide: coordinates ~2.6e-2 on the seeded synthetic weights).
+How it is used.  A single LAYER fed identical bf16 operands agrees with exact arithmetic to one bf16 ulp (2^-8; asserted in
+tests/test_gpu_conv_layers.py).  Across a 12- or 14-layer stack that does not extend to bit-level agreement: fp32-vs-fp64
+accumulation noise (~1e-6) flips the occasional activation that sits on a bf16 rounding boundary, each flip perturbs every
+downstream sum by a fraction of an ulp, which flips more activations -- two correct bf16 implementations are two independent
+draws of the same rounding noise (measured on a B200: kernels vs this model 1.5e-2, either of them vs the exact oracle
+2.6e-2, on SCoordNet's coordinate maps with the seeded synthetic weights).  So the model is a YARDSTICK, not a bit-exact
+target: the bf16 tests (tests/test_gpu_networks.py, smoke(), bench.py's parity block) require the kernels' error against the
+EXACT oracle to stay within a factor of the model's own error against the exact oracle (2 on a max-norm, 1.5 on a 99th
+percentile): the kernels may lose nothing beyond what bf16 storage itself costs.
 
 Roundings mirrored from the product (kfnet_b200/csrc/kfn_api.cu, conv_tc.cu, pointwise.cu):
   * first layers (SCoordNet conv1a, tower feat1): operand = u8 - 128 (exact), weights = bf16(fp32(w * 0.00625));

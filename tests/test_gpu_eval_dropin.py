@@ -51,6 +51,13 @@ def test_eval_cli_matches_oracle_on_files(tmp_path, weights, capsys):
         assert err < 1e-4, (t, err)
         np.testing.assert_allclose(np.log(got[..., 3]), np.log(want[..., 3]), atol=1e-4)
     assert len(dists[0]) == T and all(np.isfinite(dists[2]))
+    # --show (eval.py:121,127-160): the twelve panels per frame instead of the .npy
+    d_show = tmp_path / "show"; d_show.mkdir()
+    ev.eval(str(d_in / "image_list.txt"), str(d_in / "label_list.txt"), str(d_in / "transform.txt"), snapshot, scene="stairs",
+            output_folder=str(d_show), mode="fp32", chunk=4, quiet=True, show=True)
+    pan = np.load(d_show / "show_3.npz")
+    assert len(pan.files) == 12 and pan["kf_coord"].shape == (60, 80, 3) and not (d_show / "coord_3.npy").exists()
+    np.testing.assert_allclose(pan["kf_coord"], np.load(d_out / "coord_3.npy")[..., :3], rtol=0, atol=1e-6)
     # the printed per-frame scalars (eval.py:113-118): losses / accuracies score the ONE estimated frame against BOTH labels
     # of the iteration's batch-of-2 (KFNet.py:214 broadcast), distances against the estimated frame's own label
     import re

@@ -52,7 +52,7 @@ def test_losses_gradients_and_two_adam_steps_match_the_oracle(weights, oracle_tw
     for k in ("measure_accuracy", "temporal_accuracy", "kf_accuracy"):
         assert abs(s0[k] - o["scal1"][k]) <= 1.5 / (4 * 8 * 12), (k, s0[k], o["scal1"][k])     # at most one pixel on the 5 cm threshold
     reg = float(TO.l2_regularization({k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in weights.items()}, WD))
-    assert abs(s0["reg_loss"] - reg) <= 1e-5 * reg and abs(s0["lr"] - LR) < 1e-12
+    assert abs(s0["reg_loss"] - reg) <= 1e-5 * reg and abs(s0["lr"] - LR) < 1e-9       # (lr is reported as fp32)
     # gradient of every variable (the oracle's gradient includes the regulariser term wd * w; the kernel adds it inside Adam)
     worst = {}
     for name in weights:
@@ -85,7 +85,7 @@ def test_losses_gradients_and_two_adam_steps_match_the_oracle(weights, oracle_tw
     w1_np = {k: v.numpy() for k, v in o["w1"].items()}
     s2 = eng.train_step(d_imgs, d_gt, d_mask, LR, WD, DECAY, GAMMA)
     assert abs(s2["loss"] - o["scal2"]["loss"]) <= 2e-4 * max(1.0, abs(o["scal2"]["loss"])), (s2["loss"], o["scal2"]["loss"])
-    assert abs(s2["lr"] - LR * GAMMA ** (1 / DECAY)) < 1e-10          # exponential_decay at global_step 1
+    assert abs(s2["lr"] - LR * GAMMA ** (1 / DECAY)) < 1e-9           # exponential_decay at global_step 1
     check_update(w1_np, o["w2"], "step 2")
     # Adam moments after two steps
     for name in ("ScoreNet/conv1a/kernel", "Temporal/conv6/kernel", "Temporal/upconv1/kernel", "Temporal/uncertainty/bias"):
@@ -121,24 +121,30 @@ def test_frozen_flownet_and_kfnet_loss_surface(weights, oracle_two_steps):
     eng.close()
 
 
-def test_training_reduces_the_loss_and_commit_feeds_inference(weights):
-    """A few steps on one fixed window must lower the loss; kfn_train_commit makes the inference entry points run the trained
-    parameters (checked against the oracle's forward on the fetched weights)."""
+def test_training_follows_the_oracle_and_commit_feeds_inference(weights):
+    """Four steps on one fixed window: the loss sequence follows the oracle's (and falls: lr 1e-6 -- the case's ground truth is the
+    prediction plus noise, so the reference's 1e-4 overshoots on it, in the oracle as well); kfn_train_commit makes the inference
+    entry points run the trained parameters (checked against the oracle's forward on the fetched weights)."""
     gpu_setup()
     from kfnet_b200.train import Trainer
     from kfnet_b200 import KFNetDataSpec
     imgs, gt, mask = _case()
-    tr = Trainer(weights, KFNetDataSpec(batch_size=4, image_size=cases.SMALL_HW), base_lr=1e-4)
-    losses = [tr.step(imgs, gt.astype(np.float32), mask.astype(np.float32))["loss"] for _ in range(8)]
-    print("training losses:", ["%.4f" % v for v in losses])
-    assert losses[-1] < losses[0] and all(np.isfinite(losses))
-    assert tr.global_step == 8
+    lr = 1e-6
+    tr = Trainer(weights, KFNetDataSpec(batch_size=4, image_size=cases.SMALL_HW), base_lr=lr, weight_decay=WD, stepvalue=DECAY, gamma=GAMMA)
+    losses = [tr.step(imgs, gt.astype(np.float32), mask.astype(np.float32))["loss"] for _ in range(4)]
+    state, cur, want = {}, weights, []
+    for _ in range(4):
+        new, scal, _ = TO.train_step(cur, imgs, gt, mask, state, lr, WD, DECAY, GAMMA)
+        want.append(scal["loss"]); cur = {k: v.numpy() for k, v in new.items()}
+    print("training losses:", ["%.5f" % v for v in losses], "oracle:", ["%.5f" % v for v in want])
+    assert all(abs(a - b) <= 2e-4 * abs(b) for a, b in zip(losses, want)), (losses, want)
+    assert losses[-1] < losses[0] and want[-1] < want[0] and tr.global_step == 4
     tr.engine.train_commit()
     new_w = tr.weights()
     got = tr.engine.scoordnet(torch.from_numpy(np.ascontiguousarray(imgs)).to(torch.uint8).cuda()).cpu()
     c64, u64 = O.scoordnet(imgs.astype(np.float32), new_w, torch.float64)
     assert rms_rel_err(got[..., :3], c64) <= 1e-4 and rms_rel_err(torch.log(got[..., 3:4]), torch.log(u64)) <= 1e-4
-    assert rms_rel_err(got[..., :3], O.scoordnet(imgs.astype(np.float32), weights, torch.float64)[0]) > 1e-4   # it did change
+    assert rms_rel_err(got[..., :3], O.scoordnet(imgs.astype(np.float32), weights, torch.float64)[0]) > 1e-5   # it did change
 
 
 def test_one_full_resolution_step_runs(weights):

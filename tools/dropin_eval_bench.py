@@ -43,7 +43,7 @@ def make_scene(d, T, seed=4):
     np.savetxt(os.path.join(d, "transform.txt"), synth.make_transform(2))
 
 
-def run(frames=256, mode="bf16", chunk=64, workdir=None, quiet=True, engine=None, weights=None, repeats=2):
+def run(frames=256, mode="bf16", chunk=32, workdir=None, quiet=True, engine=None, weights=None, repeats=2):
     from kfnet_b200 import eval as ev
     from kfnet_b200 import synth
     from kfnet_b200.engine import Engine
@@ -65,6 +65,7 @@ def run(frames=256, mode="bf16", chunk=64, workdir=None, quiet=True, engine=None
         return {"value": runs[-1]["frames_per_s"], "unit": "frames/s", "frames": frames, "seconds": runs[-1]["seconds"],
                 "first_pass_frames_per_s": runs[0]["frames_per_s"], "npy_written": n_out, "mode": mode, "chunk": chunk,
                 "host_threads": min(64, os.cpu_count() or 4), "scene_write_s": t_make,
+                "breakdown_s": {k: round(runs[-1][k], 4) for k in ("wait_decode_s", "cabi_call_s", "host_metrics_s", "drain_saves_s") if k in runs[-1]},
                 "api": "kfnet_b200.eval.eval(image_list, label_list, transform_file, snapshot): PNG decode + label reads + "
                        "kfn_eval_stream_host per chunk + metrics + coord_<idx>.npy, quiet=%s" % quiet}
     finally:
@@ -76,7 +77,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--mode", default="bf16")
-    ap.add_argument("--chunk", type=int, default=64)
+    ap.add_argument("--chunk", type=int, default=32)
     ap.add_argument("--dir", default=None)
     ap.add_argument("--print_lines", action="store_true")
     a = ap.parse_args()
