@@ -165,14 +165,17 @@ def load_label8(path, image_size):
 
 
 def _frame_metrics(coords, gt, mask):
-    """dist_error (eval.py:17-29) vectorised over a chunk: coords/gt [n,h,w,3], mask [n,h,w,1] -> median cm per frame."""
-    d = np.sqrt(np.square(coords - gt).sum(-1)) * mask[..., 0]
-    d = np.where(d > 0, d, np.nan).reshape(d.shape[0], -1)
-    with np.errstate(all="ignore"):
-        import warnings
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore", category=RuntimeWarning)
-            return np.nanmedian(d, axis=1) * 100.0
+    """dist_error (eval.py:17-29) vectorised over a chunk: coords/gt [n,h,w,3], mask [n,h,w,1] -> median cm per frame
+    (np.median semantics over the pixels with mask * dist > 0; nan when there is none)."""
+    d = (np.sqrt(np.square(coords - gt).sum(-1)) * mask[..., 0]).reshape(coords.shape[0], -1)
+    valid = d > 0
+    cnt = valid.sum(1)
+    dd = np.where(valid, d, np.inf)
+    dd.sort(axis=1)
+    rows = np.arange(d.shape[0])
+    lo, hi = np.maximum(cnt - 1, 0) // 2, cnt // 2
+    med = 0.5 * (dd[rows, lo] + dd[rows, np.minimum(hi, d.shape[1] - 1)])
+    return np.where(cnt > 0, med, np.nan) * 100.0
 
 
 def eval(image_list, label_list, transform_file, snapshot, scene="stairs", output_folder="", NIS=False,  # noqa: A001
@@ -237,30 +240,10 @@ def eval(image_list, label_list, transform_file, snapshot, scene="stairs", outpu
             prev = p[1]
         return True
 
-    n_chunks = (n_iter + chunk - 1) // chunk
-    nxt = plan(0) if n_chunks else None
-    carry, last_cur, state = None, None, None
-    t_start = time.perf_counter()
-    t_dec = t_gpu = t_met = 0.0            # where the loop's wall time goes: waiting for the decoder, the C-ABI call, host metrics
-    for ci in range(n_chunks):
-        its, pairs, futs_i, futs_l = nxt
-        t0 = time.perf_counter()
-        for f in futs_i:
-            f.result()
-        t_dec += time.perf_counter() - t0
-        host_imgs = stage[ci & 1][:len(its)]
-        nxt = plan(ci + 1) if ci + 1 < n_chunks else None           # decode chunk ci+1 while the GPU runs chunk ci
-        t0 = time.perf_counter()
-        if consecutive(its, pairs, last_cur):
-            out_t, diag, carry = engine.eval_stream_host(host_imgs, its[0], transform, carry, reinit_period=period, nis_gate=NIS,
-                                                         want_diag=True, capacity=chunk)
-            out_map = out_t.numpy()
-            meas_np, temp, kf, nis = (diag[k].numpy() for k in ("measure", "temp", "kf", "nis"))
-        else:
-            out_map, meas_np, temp, kf, nis, carry = _eval_chunk_general(engine, host_imgs, pairs, its[0], transform, carry, period, NIS)
-        t_gpu += time.perf_counter() - t0
-        t0 = time.perf_counter()
-        last_cur = pairs[-1][1]
+    post = ThreadPoolExecutor(max_workers=1)
+    post_futs = []
+
+    def postprocess(its, pairs, futs_l, out_map, meas_np, temp, kf, nis):
         lab = {f: fut.result() for f, fut in futs_l.items()}
         gt = np.stack([lab[p[1]][..., :3] for p in pairs])
         mask = np.stack([lab[p[1]][..., 3:4] for p in pairs])
@@ -290,17 +273,47 @@ def eval(image_list, label_list, transform_file, snapshot, scene="stairs", outpu
                 _show_panels(os.path.join(save_dir, "show_" + str(p[1])), mask[k], gt[k], nis[k], meas_np[k], t_meas[k], temp[k], t_temp[k],
                              kf[k], out_map[k])
         elif save_dir:                                                                     # eval.py:122-126
-            maps = out_map.astype(np.float32, copy=True)
             for k, p in enumerate(pairs):
-                pool.submit(np.save, os.path.join(save_dir, "coord_" + str(p[1]) + ".npy"), maps[k])
-        t_met += time.perf_counter() - t0
+                pool.submit(np.save, os.path.join(save_dir, "coord_" + str(p[1]) + ".npy"), out_map[k].astype(np.float32, copy=False))
+
+    n_chunks = (n_iter + chunk - 1) // chunk
+    nxt = plan(0) if n_chunks else None
+    carry, last_cur, state = None, None, None
+    t_start = time.perf_counter()
+    t_dec = t_gpu = 0.0                    # where the loop's wall time goes: waiting for the decoder, the C-ABI call (+ drains at the end)
+    for ci in range(n_chunks):
+        its, pairs, futs_i, futs_l = nxt
+        t0 = time.perf_counter()
+        for f in futs_i:
+            f.result()
+        t_dec += time.perf_counter() - t0
+        host_imgs = stage[ci & 1][:len(its)]
+        nxt = plan(ci + 1) if ci + 1 < n_chunks else None           # decode chunk ci+1 while the GPU runs chunk ci
+        t0 = time.perf_counter()
+        if consecutive(its, pairs, last_cur):
+            out_t, diag, carry = engine.eval_stream_host(host_imgs, its[0], transform, carry, reinit_period=period, nis_gate=NIS,
+                                                         want_diag=True, capacity=chunk)
+            out_map = out_t.numpy()
+            meas_np, temp, kf, nis = (diag[k].numpy() for k in ("measure", "temp", "kf", "nis"))
+        else:
+            out_map, meas_np, temp, kf, nis, carry = _eval_chunk_general(engine, host_imgs, pairs, its[0], transform, carry, period, NIS)
+        t_gpu += time.perf_counter() - t0
+        last_cur = pairs[-1][1]
+        # metrics, printing and the .npy writes of this chunk run on a worker thread (in chunk order) while the GPU evaluates the next
+        # chunk; the staging views are reused by the next call, so the worker gets copies
+        post_futs.append(post.submit(postprocess, its, pairs, futs_l, out_map.copy(), meas_np.copy(), temp.copy(), kf.copy(), nis.copy()))
+    t0 = time.perf_counter()
+    for f in post_futs:
+        f.result()
+    post.shutdown(wait=True)
+    t_met = time.perf_counter() - t0
     t0 = time.perf_counter()
     pool.shutdown(wait=True)
     t_tail = time.perf_counter() - t0
     dt = time.perf_counter() - t_start
     if stats is not None:
         stats.update(frames=n_iter, seconds=dt, frames_per_s=n_iter / dt if dt > 0 else float("nan"),
-                     wait_decode_s=t_dec, cabi_call_s=t_gpu, host_metrics_s=t_met, drain_saves_s=t_tail)
+                     wait_decode_s=t_dec, cabi_call_s=t_gpu, drain_postprocess_s=t_met, drain_saves_s=t_tail)
     if not quiet:
         print("Median dist error: ", *[np.median(d) for d in dists])
         print("Mean dist error: ", *[np.mean(d) for d in dists])

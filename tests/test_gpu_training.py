@@ -14,7 +14,13 @@ from tests.util import gpu_setup, rms_rel_err
 
 pytestmark = pytest.mark.gpu
 WD, LR, DECAY, GAMMA = 1e-4, 1e-4, 80000, 0.5
-GRAD_TOL = 2e-4        # fp32 backward through up to 12 + 14 layers vs fp64 autograd, rms-relative per variable
+GRAD_TOL = 2e-4        # fp32 backward vs fp64 autograd, rms-relative per variable -- where the objective is smooth.
+# The reference's objective is NOT smooth: tf.minimum(loss_map, -2) switches pixels on and off, the sampler's floor() switches taps, every
+# ReLU switches units.  A decision that sits within fp32 noise of its threshold flips between fp32 and fp64 and moves whole gradient tensors
+# by ~1e-3 (one pixel of ~300 entering or leaving the loss).  The yardstick for that is the oracle's OWN fp32-vs-fp64 gradient difference
+# ("build it twice: fp64 truth and fp32 expected-noise yardstick"): measured 1e-3 L2 / up to 9e-2 max-norm on SCoordNet's early
+# layers, 1e-5 elsewhere.  Per variable the kernels must stay within GRAD_TOL or 3x that yardstick.
+NOISE_FACTOR = 3.0
 
 
 def _case():
@@ -29,12 +35,12 @@ def _dev(imgs, gt, mask):
 
 
 @pytest.fixture(scope="module")
-def oracle_two_steps(weights):
+def oracle_two_steps(weights):      # (one fp64 step + the fp32 yardstick; the name is kept for the tests that share it)
     imgs, gt, mask = _case()
     state = {}
     w1, scal1, grads1 = TO.train_step(weights, imgs, gt, mask, state, LR, WD, DECAY, GAMMA)
-    w2, scal2, grads2 = TO.train_step({k: v.numpy() for k, v in w1.items()}, imgs, gt, mask, state, LR, WD, DECAY, GAMMA)
-    return dict(w1=w1, scal1=scal1, grads1=grads1, w2=w2, scal2=scal2, grads2=grads2)
+    _, _, grads1_fp32 = TO.train_step(weights, imgs, gt, mask, {}, LR, WD, DECAY, GAMMA, dtype=torch.float32)     # the noise yardstick
+    return dict(w1=w1, scal1=scal1, grads1=grads1, grads1_fp32=grads1_fp32)
 
 
 def test_losses_gradients_and_two_adam_steps_match_the_oracle(weights, oracle_two_steps):
@@ -54,45 +60,61 @@ def test_losses_gradients_and_two_adam_steps_match_the_oracle(weights, oracle_tw
     reg = float(TO.l2_regularization({k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in weights.items()}, WD))
     assert abs(s0["reg_loss"] - reg) <= 1e-5 * reg and abs(s0["lr"] - LR) < 1e-9       # (lr is reported as fp32)
     # gradient of every variable (the oracle's gradient includes the regulariser term wd * w; the kernel adds it inside Adam)
-    worst = {}
+    worst, noise, bad = {}, {}, {}
     for name in weights:
-        want = o["grads1"][name].numpy() - WD * np.asarray(weights[name], np.float64)
+        reg_term = WD * np.asarray(weights[name], np.float64)
+        want = o["grads1"][name].numpy() - reg_term
         got = eng.train_get(name, "grad")
+        if name == "Temporal/prediction/bias":
+            # softmax is invariant to a constant added to all 64 logits: this gradient is exactly 0; both fp32 results are rounding dust
+            assert np.abs(want).max() < 1e-12 and np.abs(got).max() < 1e-6, (name, got, want)
+            continue
         worst[name] = rms_rel_err(got, want)
-    bad = {k: v for k, v in worst.items() if not v <= GRAD_TOL}
-    print("gradient errors (rms-relative): max %.2e at %s; median %.2e" % (max(worst.values()), max(worst, key=worst.get),
-                                                                          float(np.median(list(worst.values())))))
+        noise[name] = rms_rel_err(o["grads1_fp32"][name].double().numpy() - reg_term, want)
+        if not worst[name] <= max(GRAD_TOL, NOISE_FACTOR * noise[name]):
+            bad[name] = (worst[name], noise[name])
+    smooth = [k for k in worst if noise[k] <= GRAD_TOL / NOISE_FACTOR]
+    print("gradient errors vs fp64 autograd (rms-relative): median %.2e; %d of %d variables have an fp32 yardstick below %.0e and the kernels' max "
+          "over those is %.2e; worst overall %.2e at %s (oracle's own fp32 noise there: %.2e)"
+          % (float(np.median(list(worst.values()))), len(smooth), len(worst), GRAD_TOL / NOISE_FACTOR, max(worst[k] for k in smooth),
+             max(worst.values()), max(worst, key=worst.get), noise[max(worst, key=worst.get)]))
     assert not bad, bad
+    assert len(smooth) >= 25        # the variables in the smooth regime are held to GRAD_TOL itself
     # parameters untouched by a forward/backward-only call
     np.testing.assert_array_equal(eng.train_get("ScoreNet/conv4b/kernel"), np.asarray(weights["ScoreNet/conv4b/kernel"], np.float32))
 
-    def check_update(prev, new_oracle, tag):
-        # Adam's first steps move every parameter by about lr * sign(g): compare the UPDATES, in units of the learning rate
-        worst_u = 0.0
-        for name in weights:
-            got = eng.train_get(name).astype(np.float64) - np.asarray(prev[name], np.float64)
-            want = new_oracle[name].numpy() - np.asarray(prev[name], np.float64)
-            e = np.abs(got - want).max() / LR
-            worst_u = max(worst_u, e)
-            # fp32 storage of the parameter itself limits the resolvable update: ulp(|p|) / lr
-            ulp = np.spacing(np.abs(np.asarray(prev[name], np.float32)).max()) / LR
-            assert e <= 2e-2 + 2 * ulp, (tag, name, e, ulp)
-        print(f"{tag}: worst parameter-update error = {worst_u:.2e} learning rates")
-
-    s1 = eng.train_step(d_imgs, d_gt, d_mask, LR, WD, DECAY, GAMMA)
-    assert abs(s1["loss"] - o["scal1"]["loss"]) <= 1e-4 * max(1.0, abs(o["scal1"]["loss"]))
-    check_update(weights, o["w1"], "step 1")
-    w1_np = {k: v.numpy() for k, v in o["w1"].items()}
-    s2 = eng.train_step(d_imgs, d_gt, d_mask, LR, WD, DECAY, GAMMA)
-    assert abs(s2["loss"] - o["scal2"]["loss"]) <= 2e-4 * max(1.0, abs(o["scal2"]["loss"])), (s2["loss"], o["scal2"]["loss"])
-    assert abs(s2["lr"] - LR * GAMMA ** (1 / DECAY)) < 1e-9           # exponential_decay at global_step 1
-    check_update(w1_np, o["w2"], "step 2")
-    # Adam moments after two steps
-    for name in ("ScoreNet/conv1a/kernel", "Temporal/conv6/kernel", "Temporal/upconv1/kernel", "Temporal/uncertainty/bias"):
-        m = eng.train_get(name, "m")
-        g1 = o["grads1"][name].numpy(); g2 = o["grads2"][name].numpy()
-        want_m = 0.9 * (0.1 * g1) + 0.1 * g2
-        assert rms_rel_err(m, want_m) <= 5e-3, (name, rms_rel_err(m, want_m))
+    # The optimiser, exactly: AdamOptimizer's first steps move a parameter by ~lr * sign(g), so an element whose gradient is rounding dust
+    # moves by +-lr depending on the dust (the oracle's own fp32 and fp64 runs differ by 2 lr on such elements).  The kernel is therefore
+    # checked against the TF-1.13 formulas applied to ITS OWN fetched gradients (the gradients themselves were compared above), and the
+    # end-to-end semantics by the loss trajectory of test_training_follows_the_oracle.
+    names = ("ScoreNet/conv1a/kernel", "ScoreNet/conv4b/bias", "ScoreNet/prediction/kernel", "Temporal/feat3/kernel", "Temporal/conv6/kernel",
+             "Temporal/upconv1/kernel", "Temporal/uncertainty/bias", "Temporal/fc1/kernel")
+    b1, b2, eps = 0.9, 0.999, 1e-8
+    p_prev = {n: np.asarray(weights[n], np.float64) for n in names}
+    m_prev = {n: np.zeros_like(p_prev[n]) for n in names}
+    v_prev = {n: np.zeros_like(p_prev[n]) for n in names}
+    for t in (1, 2):
+        st = eng.train_step(d_imgs, d_gt, d_mask, LR, WD, DECAY, GAMMA)
+        lr = LR * GAMMA ** ((t - 1) / DECAY)                                    # exponential_decay at global_step t-1 (train.py:306-310)
+        assert abs(st["lr"] - lr) < 1e-9
+        if t == 1:      # (after an lr = 1e-4 step the two runs sit on different sides of many switches; the lr = 1e-6 trajectory is compared below)
+            assert abs(st["loss"] - o["scal1"]["loss"]) <= 1e-4 * max(1.0, abs(o["scal1"]["loss"])), (st["loss"], o["scal1"]["loss"])
+        lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+        for n in names:
+            g = eng.train_get(n, "grad").astype(np.float64) + WD * p_prev[n]     # + l2_regularizer gradient
+            m = b1 * m_prev[n] + (1 - b1) * g
+            v = b2 * v_prev[n] + (1 - b2) * g * g
+            p = p_prev[n] - lr_t * m / (np.sqrt(v) + eps)
+            got_p, got_m, got_v = (eng.train_get(n, w_).astype(np.float64) for w_ in ("param", "m", "v"))
+            np.testing.assert_allclose(got_m, m, rtol=2e-6, atol=1e-12, err_msg=f"step {t} {n} m")
+            np.testing.assert_allclose(got_v, v, rtol=4e-6, atol=1e-20, err_msg=f"step {t} {n} v")
+            # the update in units of lr_t: m / (sqrt(v) + eps) is O(1); fp32 storage of p bounds what can be resolved
+            upd = (got_p - p_prev[n]) / lr_t
+            want = (p - p_prev[n]) / lr_t
+            ulp = np.spacing(np.abs(p_prev[n]).astype(np.float32)).astype(np.float64) / lr_t
+            assert np.all(np.abs(upd - want) <= 1e-5 + ulp), (t, n, float(np.abs(upd - want).max()))
+            p_prev[n], m_prev[n], v_prev[n] = got_p, got_m, got_v
+    print("Adam: parameters, m and v of two consecutive steps follow the TF-1.13 formulas on the kernels' own gradients (8 variables)")
     eng.close()
 
 

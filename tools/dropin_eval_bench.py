@@ -65,7 +65,7 @@ def run(frames=256, mode="bf16", chunk=32, workdir=None, quiet=True, engine=None
         return {"value": runs[-1]["frames_per_s"], "unit": "frames/s", "frames": frames, "seconds": runs[-1]["seconds"],
                 "first_pass_frames_per_s": runs[0]["frames_per_s"], "npy_written": n_out, "mode": mode, "chunk": chunk,
                 "host_threads": min(64, os.cpu_count() or 4), "scene_write_s": t_make,
-                "breakdown_s": {k: round(runs[-1][k], 4) for k in ("wait_decode_s", "cabi_call_s", "host_metrics_s", "drain_saves_s") if k in runs[-1]},
+                "breakdown_s": {k: round(runs[-1][k], 4) for k in ("wait_decode_s", "cabi_call_s", "drain_postprocess_s", "drain_saves_s") if k in runs[-1]},
                 "api": "kfnet_b200.eval.eval(image_list, label_list, transform_file, snapshot): PNG decode + label reads + "
                        "kfn_eval_stream_host per chunk + metrics + coord_<idx>.npy, quiet=%s" % quiet}
     finally:
