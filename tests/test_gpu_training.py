@@ -89,7 +89,9 @@ def test_losses_gradients_and_two_adam_steps_match_the_oracle(weights, oracle_tw
     # end-to-end semantics by the loss trajectory of test_training_follows_the_oracle.
     names = ("ScoreNet/conv1a/kernel", "ScoreNet/conv4b/bias", "ScoreNet/prediction/kernel", "Temporal/feat3/kernel", "Temporal/conv6/kernel",
              "Temporal/upconv1/kernel", "Temporal/uncertainty/bias", "Temporal/fc1/kernel")
-    b1, b2, eps = 0.9, 0.999, 1e-8
+    # fp32 constants as the kernel (and TF's fp32 ApplyAdam) forms them: (1 - beta) is evaluated in float32
+    b1, b2, eps = float(np.float32(0.9)), float(np.float32(0.999)), 1e-8
+    omb1, omb2 = float(np.float32(1) - np.float32(0.9)), float(np.float32(1) - np.float32(0.999))
     p_prev = {n: np.asarray(weights[n], np.float64) for n in names}
     m_prev = {n: np.zeros_like(p_prev[n]) for n in names}
     v_prev = {n: np.zeros_like(p_prev[n]) for n in names}
@@ -99,11 +101,11 @@ def test_losses_gradients_and_two_adam_steps_match_the_oracle(weights, oracle_tw
         assert abs(st["lr"] - lr) < 1e-9
         if t == 1:      # (after an lr = 1e-4 step the two runs sit on different sides of many switches; the lr = 1e-6 trajectory is compared below)
             assert abs(st["loss"] - o["scal1"]["loss"]) <= 1e-4 * max(1.0, abs(o["scal1"]["loss"])), (st["loss"], o["scal1"]["loss"])
-        lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+        lr_t = lr * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
         for n in names:
             g = eng.train_get(n, "grad").astype(np.float64) + WD * p_prev[n]     # + l2_regularizer gradient
-            m = b1 * m_prev[n] + (1 - b1) * g
-            v = b2 * v_prev[n] + (1 - b2) * g * g
+            m = b1 * m_prev[n] + omb1 * g
+            v = b2 * v_prev[n] + omb2 * g * g
             p = p_prev[n] - lr_t * m / (np.sqrt(v) + eps)
             got_p, got_m, got_v = (eng.train_get(n, w_).astype(np.float64) for w_ in ("param", "m", "v"))
             np.testing.assert_allclose(got_m, m, rtol=2e-6, atol=1e-12, err_msg=f"step {t} {n} m")
