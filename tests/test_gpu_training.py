@@ -108,7 +108,7 @@ def test_losses_gradients_and_two_adam_steps_match_the_oracle(weights, oracle_tw
             v = b2 * v_prev[n] + omb2 * g * g
             p = p_prev[n] - lr_t * m / (np.sqrt(v) + eps)
             got_p, got_m, got_v = (eng.train_get(n, w_).astype(np.float64) for w_ in ("param", "m", "v"))
-            np.testing.assert_allclose(got_m, m, rtol=2e-6, atol=1e-12, err_msg=f"step {t} {n} m")
+            np.testing.assert_allclose(got_m, m, rtol=2e-6, atol=5e-7 * np.abs(m).max(), err_msg=f"step {t} {n} m")   # (0.9 m + 0.1 g may cancel)
             np.testing.assert_allclose(got_v, v, rtol=4e-6, atol=1e-20, err_msg=f"step {t} {n} v")
             # the update in units of lr_t: m / (sqrt(v) + eps) is O(1); fp32 storage of p bounds what can be resolved
             upd = (got_p - p_prev[n]) / lr_t
