@@ -47,6 +47,20 @@ NUM_SEQUENCES = 8           # BASELINE configs[4]: 8 x 256-frame sequences
 METRIC = "frames/sec at 480x640 (60x80 label grid)"
 
 
+def scoordnet_algorithmic_bytes(B, H=480, W=640):
+    """One read of each layer's input + one write of its output (bf16 between layers, u8 frames in, fp32 map out) + the bf16 weights once:
+    the bytes the SCoordNet stack has to move per batch if nothing is re-read (cnn_wrapper/SCoordNet.py:21-32)."""
+    layers = [(3, 3, 64, 1), (3, 64, 64, 1), (3, 64, 256, 2), (3, 256, 256, 1), (3, 256, 512, 2), (3, 512, 512, 1), (3, 512, 1024, 2),
+              (3, 1024, 1024, 1), (3, 1024, 512, 1), (3, 512, 256, 1), (1, 256, 128, 1), (1, 128, 4, 1)]
+    px, total = B * H * W, 0
+    for i, (k, cin, cout, s) in enumerate(layers):
+        in_b = px * cin * (1 if i == 0 else 2)
+        px //= s * s
+        out_b = px * cout * (4 if i == len(layers) - 1 else 2)
+        total += in_b + out_b + k * k * cin * cout * 2
+    return total
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -409,7 +423,8 @@ def run_ours(args):
         if args.ncu and world == 1 and args.mode == "bf16":
             traffic, traffic_why = ncu_scoordnet_traffic(B, n_sc)
         if traffic:
-            traffic["algorithmic_bytes"] = "see DESIGN.md 4.1: weights + one read + one write of each layer's activations"
+            traffic["algorithmic_bytes"] = scoordnet_algorithmic_bytes(B)
+            traffic["ratio"] = traffic["bytes"] / traffic["algorithmic_bytes"]
         parity = None
         if world == 1 and args.parity_frames > 0 and args.mode == "bf16":
             parity = parity_block(args, eng, weights, Tm, dev0, T, H, W)
