@@ -220,6 +220,8 @@ KFN_API int kfn_train_step(kfn_handle* h, const uint8_t* images, const float* gt
                    float weight_decay, int decay_steps, float gamma, int apply_update, float* scalars_host, void* stream);
 KFN_API int kfn_train_get(kfn_handle* h, const char* name, int what, float* host_out, int64_t n);
 KFN_API int kfn_train_commit(kfn_handle* h);
+/* Sets global_step (train.py:361-362,375 `global_step.assign(step)`, --reset_step): the learning-rate decay exponent. */
+KFN_API int kfn_train_set_step(kfn_handle* h, int step);
 
 /* Number of kernels launched through this handle's entry points since the last reset (bench.py's gpu_launches);
  * h == NULL: every kernel the calling thread launched through the library, handle-less entry points included. */

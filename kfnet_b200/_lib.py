@@ -37,6 +37,7 @@ SIGNATURES = {
     "kfn_train_step": (_i, [_vp, _vp, _vp, _vp, C.c_float, C.c_float, _i, C.c_float, _i, _vp, _vp]),
     "kfn_train_get": (_i, [_vp, C.c_char_p, _i, _vp, _i64]),
     "kfn_train_commit": (_i, [_vp]),
+    "kfn_train_set_step": (_i, [_vp, _i]),
     "kfn_launch_count": (_i64, [_vp, _i]),
 }
 

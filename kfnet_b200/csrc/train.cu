@@ -486,7 +486,8 @@ struct TrainState {
   int64_t w_off[kNumLayers], b_off[kNumLayers];
   LayerOps ops[kNumLayers];
   int64_t packed_elems = 0;
-  int step = 0;                                    // global_step (train.py:305)
+  int step = 0;                                    // global_step (train.py:305): learning-rate decay exponent
+  int adam_t = 0;                                  // updates applied since kfn_train_begin (AdamOptimizer's beta^t accumulators start fresh)
   // activations / gradients / scratch (one cudaMalloc)
   float* arena = nullptr;
   int64_t arena_elems = 0;
@@ -947,7 +948,7 @@ int kfn_train_step(kfn_handle* h, const uint8_t* images, const float* gt8, const
   KFN_CUDA_OK(cudaMemcpyAsync(ssq.data(), t->sumsq_partial, 2048 * sizeof(float), cudaMemcpyDeviceToHost, st));
   const double lr = (double)base_lr * std::pow((double)gamma, (double)t->step / (double)(decay_steps > 0 ? decay_steps : 1));   // exponential_decay
   if (apply_update) {
-    const int tstep = t->step + 1;
+    const int tstep = t->adam_t + 1;
     const double b1 = 0.9, b2 = 0.999;
     const float lr_t = (float)(lr * std::sqrt(1.0 - std::pow(b2, tstep)) / (1.0 - std::pow(b1, tstep)));
     for (int r = 0; r < 2; ++r) {
@@ -956,7 +957,8 @@ int kfn_train_step(kfn_handle* h, const uint8_t* images, const float* gt8, const
                                        ranges[r].n, weight_decay, lr_t, (float)b1, (float)b2, 1e-8f);
       KFN_LAUNCH_OK();
     }
-    t->step = tstep;
+    t->adam_t = tstep;
+    t->step += 1;
   }
   KFN_CUDA_OK(cudaStreamSynchronize(st));
   if (scalars_host) {
@@ -988,6 +990,14 @@ int kfn_train_get(kfn_handle* h, const char* name, int what, float* host_out, in
   const float* src = what == 0 ? t->params : what == 1 ? t->grads : what == 2 ? t->adam_m : what == 3 ? t->adam_v : nullptr;
   KFN_REQUIRE(src, "what must be 0..3");
   KFN_CUDA_OK(cudaMemcpy(host_out, src + (bias ? t->b_off[li] : t->w_off[li]), (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+  return KFN_OK;
+}
+
+// global_step of the optimiser (train.py:361-362,375: `init_step = global_step.assign(step)`; --reset_step): drives the learning-rate decay
+// only -- Adam's bias correction counts the updates applied since kfn_train_begin, like a freshly built AdamOptimizer
+int kfn_train_set_step(kfn_handle* h, int step) {
+  KFN_REQUIRE(h && h->train && step >= 0, "kfn_train_begin not called / negative step");
+  h->train->step = step;
   return KFN_OK;
 }
 

@@ -286,6 +286,10 @@ class Engine:
                                           out.ctypes.data_as(C.c_void_p), out.size))
         return out
 
+    def train_set_step(self, step):
+        """global_step.assign(step) (train.py:361-362,375; --reset_step)."""
+        _lib.check(self.lib.kfn_train_set_step(self.h, int(step)))
+
     def train_commit(self):
         """Trained parameters -> the weight set the inference entry points use."""
         _lib.check(self.lib.kfn_train_commit(self.h))

@@ -40,6 +40,22 @@ def training_groups(scene):
     return groups
 
 
+def initial_weights(seed=None):
+    """`sess.run(init_op)` (train.py:396-399) when no snapshot is given: tf.layers' defaults -- glorot_uniform kernels
+    (limit = sqrt(6 / (fan_in + fan_out)), fans taken from the last two dims x the receptive field) and zero biases."""
+    from .synth import weight_shapes
+    rng = np.random.default_rng(seed)
+    w = {}
+    for name, shape in weight_shapes().items():
+        if name.endswith("/bias"):
+            w[name] = np.zeros(shape, np.float32)
+            continue
+        rec = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+        lim = np.sqrt(6.0 / (shape[-2] * rec + shape[-1] * rec))
+        w[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+    return w
+
+
 def prepare_window(labels_full, transform_inv):
     """train.py:273-280: nearest-neighbour /8 of labels and masks, mask == 1.0, labels moved into the network's frame with
     ApplyTransform(gt, transform, inverse=True) where `transform` = get_transform() = inv(transform.txt) -- i.e. gt is
@@ -55,14 +71,16 @@ class Trainer:
     """`run` + `solver` of train.py on one Engine.  step() returns the scalars the reference prints every DISPLAY steps."""
 
     def __init__(self, weights, spec=None, train_scoordnet=True, fix_flownet=False, base_lr=BASE_LR, weight_decay=WEIGHT_DECAY,
-                 stepvalue=None, gamma=GAMMA, device=None, engine=None):
+                 stepvalue=None, gamma=GAMMA, device=None, engine=None, step=0):
         from .engine import Engine
         self.spec = spec or KFNetDataSpec()
         self.engine = engine or Engine(weights, mode="fp32", image_size=self.spec.image_size, device=device)
         self.base_lr, self.weight_decay, self.gamma = base_lr, weight_decay, gamma
         self.stepvalue = stepvalue if stepvalue is not None else STEPVALUE.get(self.spec.scene, 80000)
         self.engine.train_begin(self.spec.batch_size, train_scoordnet, not fix_flownet)   # train.py:283-285
-        self.global_step = 0
+        self.global_step = int(step)
+        if self.global_step:
+            self.engine.train_set_step(self.global_step)                                  # init_step = global_step.assign(step)
 
     def step(self, images, gt_coords, masks, apply_update=True):
         """images: uint8 [B,H,W,3]; gt_coords [B,h,w,3] / masks [B,h,w,1] as prepare_window() returns them (numpy or cuda tensors)."""
@@ -88,9 +106,13 @@ class Trainer:
 
 
 def train(image_list, label_list, transform_file, snapshot=None, scene="stairs", model_folder="", max_steps=None, fix_flownet=False,
-          weights=None, display=DISPLAY, snapshot_every=SNAPSHOT, device=None, quiet=False):
+          weights=None, display=DISPLAY, snapshot_every=SNAPSHOT, device=None, quiet=False, step=0, reset_step=-1, scoordnet="",
+          oflownet=""):
     """The loop of train.py:347-420 over the scene's training windows, in order (the reference shuffles its queue with a
-    fixed seed; order only matters for reproducing a particular run)."""
+    fixed seed; order only matters for reproducing a particular run).  `step` / `reset_step` set global_step (train.py:361-362);
+    `scoordnet` / `oflownet` = model folders whose newest snapshot overrides the 'ScoreNet' / 'Temporal' scope (train.py:402-407);
+    with both given the step is reset to 4 x stepvalue like set_stepvalue does (train.py:346-348); the loop ends at
+    max_steps = 5 x stepvalue (train.py:349) unless `max_steps` says otherwise."""
     from .eval import get_transform, load_image, load_label, load_snapshot_weights, read_lines
     image_paths, label_paths = read_lines(image_list), read_lines(label_list)
     assert len(image_paths) == len(label_paths)
@@ -99,8 +121,19 @@ def train(image_list, label_list, transform_file, snapshot=None, scene="stairs",
     if not groups:
         raise ValueError("no training window fits the image list")
     Tinv = get_transform(transform_file)
-    tr = Trainer(weights if weights is not None else load_snapshot_weights(snapshot), spec, fix_flownet=fix_flownet, device=device)
-    n = max_steps if max_steps is not None else len(groups)
+    from .eval import get_snapshot
+    w = dict(weights if weights is not None else (load_snapshot_weights(snapshot) if snapshot else initial_weights()))
+    for folder, scope in ((scoordnet, "ScoreNet/"), (oflownet, "Temporal/")):           # RestoreFromScope (train.py:402-407)
+        if folder:
+            part = load_snapshot_weights(get_snapshot(folder)[0])
+            w.update({k: v for k, v in part.items() if k.startswith(scope)})
+    stepvalue = STEPVALUE.get(scene, 80000)
+    if scoordnet and oflownet and reset_step < 0:
+        reset_step = stepvalue * 4
+    if reset_step >= 0:
+        step = reset_step
+    tr = Trainer(w, spec, fix_flownet=fix_flownet, device=device, step=step, stepvalue=stepvalue)
+    n = max_steps if max_steps is not None else max(0, stepvalue * 5 - step + 1)           # while step <= FLAGS.max_steps
     hist = []
     for it in range(n):
         g = groups[it % len(groups)]
@@ -125,13 +158,16 @@ def main(argv=None):
     ap.add_argument("--scene", default="")
     ap.add_argument("--max_steps", type=int, default=None)
     ap.add_argument("--fix_flownet", action="store_true")
+    ap.add_argument("--reset_step", type=int, default=-1)
+    ap.add_argument("--scoordnet", default="", help="model folder whose ScoreNet variables are restored over the snapshot")
+    ap.add_argument("--oflownet", default="", help="model folder whose Temporal variables are restored over the snapshot")
     ap.add_argument("--gpu", type=int, default=0)
     a = ap.parse_args(argv)
     from .eval import get_snapshot
-    snapshot, _ = get_snapshot(a.model_folder)
+    snapshot, step = get_snapshot(a.model_folder)
     train(os.path.join(a.input_folder, "image_list.txt"), os.path.join(a.input_folder, "label_list.txt"),
           os.path.join(a.input_folder, "transform.txt"), snapshot, scene=a.scene, model_folder=a.model_folder, max_steps=a.max_steps,
-          fix_flownet=a.fix_flownet, device=a.gpu)
+          fix_flownet=a.fix_flownet, device=a.gpu, step=step, reset_step=a.reset_step, scoordnet=a.scoordnet, oflownet=a.oflownet)
 
 
 if __name__ == "__main__":

@@ -22,7 +22,8 @@ int main(int argc, char** argv) {
   SYM(kfn_finalize_weights); SYM(kfn_workspace_bytes); SYM(kfn_scoordnet_forward); SYM(kfn_oflow_feat_forward);
   SYM(kfn_diff_volume); SYM(kfn_oflownet_forward); SYM(kfn_kalman_scan); SYM(kfn_flow_warp_kalman);
   SYM(kfn_bilinear_sampler); SYM(kfn_apply_transform); SYM(kfn_kalman_update); SYM(kfn_sequence_extra_bytes);
-  SYM(kfn_eval_sequences); SYM(kfn_eval_sequences_host); SYM(kfn_conv_layer); SYM(kfn_launch_count);
+  SYM(kfn_eval_sequences); SYM(kfn_eval_sequences_host); SYM(kfn_eval_stream_host); SYM(kfn_conv_layer); SYM(kfn_launch_count);
+  SYM(kfn_train_begin); SYM(kfn_train_step); SYM(kfn_train_get); SYM(kfn_train_commit); SYM(kfn_train_set_step);
 
   const char* (*version)(void) = (const char* (*)(void))dlsym(lib, "kfn_version");
   const char* (*last_error)(void) = (const char* (*)(void))dlsym(lib, "kfn_last_error");

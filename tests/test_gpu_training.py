@@ -194,3 +194,36 @@ def test_one_full_resolution_step_runs(weights):
         g = eng.train_get(name, "grad")
         assert np.isfinite(g).all() and np.abs(g).max() > 0, name
     eng.close()
+
+
+def test_train_loop_on_files(tmp_path, weights):
+    """kfnet_b200.train.train() -- the loop of train.py:347-420 -- on files laid out like the reference expects: windows from
+    get_indexes(is_training=True), labels through prepare_window, two steps, snapshot written as model.ckpt-<step>.npz and
+    readable by the drop-in eval's snapshot loader."""
+    gpu_setup()
+    import cv2
+    from kfnet_b200 import eval as ev
+    from kfnet_b200 import synth
+    from kfnet_b200.train import train
+    T = 5
+    imgs, labels = synth.make_sequence(T, seed=4), synth.make_labels(T, seed=5)
+    d_in, d_model = tmp_path / "in", tmp_path / "model"
+    d_in.mkdir(); d_model.mkdir()
+    ip, lp = [], []
+    for t in range(T):
+        a, b = d_in / f"frame-{t:06d}.color.png", d_in / f"frame-{t:06d}.label.bin"
+        assert cv2.imwrite(str(a), np.ascontiguousarray(imgs[t][..., ::-1]))
+        labels[t].astype("<f4").tofile(b)
+        ip.append(str(a)); lp.append(str(b))
+    (d_in / "image_list.txt").write_text("\n".join(ip) + "\n"); (d_in / "label_list.txt").write_text("\n".join(lp) + "\n")
+    np.savetxt(d_in / "transform.txt", synth.make_transform(2))
+    synth.save_weights(str(d_model / "model.ckpt-7.npz"), weights)
+    snapshot, step = ev.get_snapshot(str(d_model))
+    tr, hist = train(str(d_in / "image_list.txt"), str(d_in / "label_list.txt"), str(d_in / "transform.txt"), snapshot, scene="stairs",
+                     model_folder=str(d_model), max_steps=2, step=step, quiet=True)
+    assert len(hist) == 2 and all(np.isfinite(list(h.values())).all() for h in hist) and tr.global_step == 9
+    assert abs(hist[1]["lr"] - 1e-4 * 0.5 ** (8 / 100000)) < 1e-9          # decay continues from the snapshot's step (stairs: stepvalue 100000)
+    new_snapshot, new_step = ev.get_snapshot(str(d_model))
+    assert new_step == 9
+    w2 = ev.load_snapshot_weights(new_snapshot)
+    assert set(w2) == set(weights) and np.abs(w2["ScoreNet/conv7/kernel"] - weights["ScoreNet/conv7/kernel"]).max() > 0
