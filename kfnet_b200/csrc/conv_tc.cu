@@ -80,6 +80,8 @@ struct __align__(8) TcParams {
   // every W limb that pairs with that A limb is a shifted-descriptor MMA on the resident weights
   int a_chunks, w_chunks, n_limbs_a, n_limbs_w;
   uint32_t term_mask[3];        // bit lw of term_mask[la]: the product (A limb la) x (W limb lw) is accumulated
+  int x3_fused;                 // non-halo limb modes: one stage holds ALL limbs of A and W for a (tap, chunk) -- every product that uses a
+                                // tile reads it from the same stage (4 tile loads per 3 products in fp16x2 instead of 6)
   int f16;                      // limbs are fp16 (KFN_MODE_FP16X2): limb 1 holds the residual scaled by 2^11
   float corr_scale;             // factor applied to the correction accumulator in the epilogue (1, or 2^-11 for fp16 limbs)
   uint32_t epi_stage_off;       // byte offset (from the 1024-aligned smem base) of the epilogue staging area
@@ -243,6 +245,27 @@ __device__ __forceinline__ void mma_role_x3(const TcParams& p, uint32_t smem_bas
     mbar_wait(smem_u32(&s_tempty[0]), ((uint32_t)j & 1u) ^ 1u);
     tc_fence_after();
     uint32_t used = 0;
+    if (p.x3_fused) {
+      const uint64_t a16 = (uint64_t)(p.a_bytes >> 4), b16 = (uint64_t)(p.b_bytes >> 4);
+      const uint64_t w_off = (uint64_t)p.n_limbs_a * a16;
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        for (int kc = 0; kc < p.cpk; ++kc) {
+          mbar_wait(smem_u32(&s_full[s]), ph);
+          tc_fence_after();
+          for (int t = 0; t < p.n_terms; ++t) {        // smallest products first, the main term last (as in the unfused order)
+            const int acc = (p.la[t] == 0 && p.lw[t] == 0) ? (tap % 3) : 3;
+            umma_kblock<KSTEPS>(tmem_base + (uint32_t)acc * p.acc_stride, adesc + (uint64_t)p.la[t] * a16, adesc + w_off + (uint64_t)p.lw[t] * b16,
+                                p.idesc, (used >> acc) & 1u);
+            used |= 1u << acc;
+          }
+          umma_commit(smem_u32(&s_empty[s]));
+          adesc += stage16;
+          if (++s == p.stages) { s = 0; ph ^= 1u; adesc = a0; }
+        }
+      }
+      umma_commit(smem_u32(&s_tfull[0]));
+      continue;
+    }
     for (int tap = 0; tap < p.ntaps; ++tap) {
       for (int t = 0; t < p.n_terms; ++t) {
         const int acc = (p.la[t] == 0 && p.lw[t] == 0) ? (tap % 3) : 3;
@@ -552,6 +575,21 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           int cw, cpar, chh, coff;
           if (p.istride == 1) { cw = w0 + dx; cpar = 0; chh = h0 + dy; coff = 0; }
           else { cw = w0 + (dx >> 1); cpar = dy & 1; chh = h0 + (dy >> 1); coff = (dx & 1) * p.in_cs; }
+          if (p.x3_fused) {
+            // stage = [A limb 0 | .. | A limb la-1 | W limb 0 | .. | W limb lw-1] of this (tap, chunk)
+            for (int kc = 0; kc < p.cpk; ++kc) {
+              mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);
+              const uint32_t full = smem_u32(&s_full[s]);
+              const uint32_t dst = smem_base + (uint32_t)s * p.stage_bytes;
+              mbar_expect_tx(full, (uint32_t)p.n_limbs_a * p.a_bytes + (uint32_t)p.n_limbs_w * p.b_bytes);
+              for (int la = 0; la < p.n_limbs_a; ++la)
+                tma_load_5d(dst + (uint32_t)la * p.a_bytes, &tmA, full, coff + la * p.in_ls + kc * p.KC, cw, cpar, chh, n0);
+              for (int lw = 0; lw < p.n_limbs_w; ++lw)
+                tma_load_3d(dst + (uint32_t)p.n_limbs_a * p.a_bytes + (uint32_t)lw * p.b_bytes, &tmB, full, lw * p.w_cin + kc * p.KC, nt * p.BN, tap);
+              if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+            continue;
+          }
           for (int t = 0; t < p.n_terms; ++t) {
             const int a_c0 = coff + p.la[t] * p.in_ls, w_c0 = p.lw[t] * p.w_cin;
             for (int kc = 0; kc < p.cpk; ++kc) {
@@ -1103,6 +1141,12 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     p.tiles_w = g.MW / bw; p.tiles_h = g.MH / bh; p.tiles_n = (g.N + bn - 1) / bn;
     p.a_bytes = (uint32_t)(kBlockM * row_bytes);
     p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
+    static const bool x3_fused_on = env_flag("KFN_TC_X3_FUSED", true);   // A/B switch: all limbs of a (tap, chunk) in one stage
+    const uint32_t fused_stage = ((uint32_t)limbs_a * p.a_bytes + (uint32_t)limbs_w * p.b_bytes + 1023u) & ~1023u;
+    if (x3 && x3_fused_on && !g.im2col_u8 && 2u * fused_stage <= budget) {
+      p.x3_fused = 1;
+      p.stage_bytes = fused_stage;
+    }
     uint32_t resident = 0;
     if (g.im2col_u8) {   // resident weight tile at the base, stages hold only the A tile the producer warps write
       p.im2col = 1; p.img = reinterpret_cast<const uint8_t*>(in);
