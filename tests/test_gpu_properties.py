@@ -87,3 +87,49 @@ def test_host_buffer_entry_point_matches_device_path(staged):
     for _ in range(3):
         out = eng.eval_sequences_host(host, Tm, reinit_period=500, frames_per_batch=5, pairs_per_batch=4)
         assert torch.equal(out, ref)
+
+
+def test_streaming_entry_point_in_ragged_chunks_is_bit_identical(staged):
+    """kfn_eval_stream_host (what the drop-in eval() calls): the sequence delivered in ragged chunks -- 1 frame, 4 frames, a chunk
+    that straddles a re-initialisation, a tail -- with the filter state and the last feature map carried on the device ==
+    one kfn_eval_sequences call, bit for bit; the diagnostics it returns are the scan's."""
+    eng, imgs, meas, _, flow_t, sigw_t = staged
+    Tm = cases.transform().astype(np.float32)
+    seq = imgs.unsqueeze(0).contiguous()
+    whole = eng.eval_sequences(seq, Tm, reinit_period=5, frames_per_batch=5, pairs_per_batch=4).cpu()[0]
+    diag_ref = eng.kalman_scan(meas, flow_t, sigw_t, Tm, reinit_period=5, diagnostics=True)
+    host = imgs.cpu().pin_memory()
+    carry, outs, temps, nises = None, [], [], []
+    for a, b in ((0, 1), (1, 5), (5, 6), (6, 11), (11, T)):
+        out, diag, carry = eng.eval_stream_host(host[a:b].contiguous().pin_memory(), a, Tm, carry, reinit_period=5, frames_per_batch=3,
+                                                pairs_per_batch=2, want_diag=True, capacity=8)
+        outs.append(out.clone()); temps.append(diag["temp"].clone()); nises.append(diag["nis"].clone())
+    assert torch.equal(torch.cat(outs), whole)
+    assert torch.equal(torch.cat(temps), diag_ref["temp"][0].cpu()) and torch.equal(torch.cat(nises), diag_ref["nis"][0].cpu())
+    # without the carry a continuing chunk must be refused, not silently warped from garbage (ADVICE r01: state_in check)
+    from kfnet_b200._lib import KfnError
+    with pytest.raises((KfnError, ValueError)):
+        eng.kalman_scan(meas[:, 2:4].contiguous(), flow_t[:, 2:4].contiguous(), sigw_t[:, 2:4].contiguous(), Tm, state_in=None, first_index=2,
+                        reinit_period=5)
+
+
+def test_edge_cases_single_frame_every_frame_reinit_and_oversized_batches(staged):
+    """T = 1 (only a re-initialisation frame: no pair exists), reinit_period = 1 (every frame is its own measurement), batches larger
+    than the job, and S = 3 ragged against the batch size."""
+    eng, imgs, meas, _, _, _ = staged
+    Tm = cases.transform().astype(np.float32)
+    one = eng.eval_sequences(imgs[:1].unsqueeze(0).contiguous(), Tm, reinit_period=500, frames_per_batch=64, pairs_per_batch=64)
+    R, tr = torch.from_numpy(Tm[:3, :3]).cuda(), torch.from_numpy(Tm[:3, 3]).cuda()
+    want0 = torch.cat([meas[0, :1, ..., :3] @ R.T + tr, 1.0 / meas[0, :1, ..., 3:4]], -1)
+    assert torch.allclose(one[0], want0, rtol=1e-5, atol=1e-5)                      # output = transformed measurement, 1 / sigma_z
+    every = eng.eval_sequences(imgs[:5].unsqueeze(0).contiguous(), Tm, reinit_period=1, frames_per_batch=64, pairs_per_batch=64)
+    want = torch.cat([meas[0, :5, ..., :3] @ R.T + tr, 1.0 / meas[0, :5, ..., 3:4]], -1)
+    assert torch.allclose(every[0], want, rtol=1e-5, atol=1e-5)
+    three = imgs[:9].reshape(3, 3, 480, 640, 3).contiguous()                        # S = 3 sequences of T = 3, batches of 4 frames / 5 pairs
+    out3 = eng.eval_sequences(three, Tm, reinit_period=500, frames_per_batch=4, pairs_per_batch=5)
+    for s_ in range(3):
+        solo = eng.eval_sequences(three[s_:s_ + 1].contiguous(), Tm, reinit_period=500, frames_per_batch=16, pairs_per_batch=16)
+        assert torch.equal(out3[s_], solo[0])
+    from kfnet_b200._lib import KfnError
+    with pytest.raises((KfnError, AssertionError)):
+        eng.eval_sequences(imgs[:0].unsqueeze(0).contiguous(), Tm)                  # empty problem -> KFN_ERR_ARG, not a launch
