@@ -727,8 +727,18 @@ int eval_sequences_impl(kfn_handle* h, const uint8_t* images, int S, int T, cons
     if (a.overflow) { set_error("workspace too small for eval_sequences"); return KFN_ERR_WORKSPACE; }
     const int64_t mark = a.off;
     if ((rc = scoordnet_impl(h, images + f0 * img_bytes, B, measure + f0 * P * 4, a, st, false, pre, f1))) return rc;
-    a.off = mark;
-    if ((rc = tower_impl(h, images + f0 * img_bytes, B, feat + f0 * P * 32, a, st, false, pre, f1))) return rc;
+    // The tower runs in sub-batches of <= 16 frames of the same batch: its small layers are fastest when a sub-batch's activations
+    // stay L2-resident, while SCoordNet wants LARGE batches (the 60x80-grid layers have 37.5 M-tiles per frame: on 148 SMs a batch of 16
+    // ends in a 20 %-filled last wave for conv6, 10 % for conv5; 71 frames = 2662.5 tiles = 17.99 waves)
+    const int TB = 16;
+    const int64_t pre_frame = (int64_t)h->H * h->W * (h->mode == KFN_MODE_FP32 ? 3 * 4 : 32 * 2);   // bytes of `pre` per frame
+    for (int b0 = 0; b0 < B; b0 += TB) {
+      const int b = (B - b0) < TB ? (B - b0) : TB;
+      a.off = mark;
+      void* pre_sub = pre ? reinterpret_cast<uint8_t*>(pre) + b0 * pre_frame : nullptr;
+      void* f1_sub = f1 ? reinterpret_cast<uint8_t*>(f1) + (int64_t)b0 * h->H * h->W * 16 * 2 : nullptr;
+      if ((rc = tower_impl(h, images + (f0 + b0) * img_bytes, b, feat + (f0 + b0) * P * 32, a, st, false, pre_sub, f1_sub))) return rc;
+    }
   }
   // 2. process system: pair (f-1, f) for every flat frame f >= 1 (f >= 0 when the chunk continues a sequence: slot 0 of
   //    featbuf then holds frame -1).  Pairs that straddle two sequences are computed and ignored (frame 0 of every

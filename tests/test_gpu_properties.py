@@ -74,6 +74,8 @@ def test_graph_replay_and_batching_are_bit_identical(staged):
     two = torch.cat([seq, seq]).contiguous()                                              # S = 2 identical sequences
     b = eng.eval_sequences(two, Tm, reinit_period=500, frames_per_batch=7, pairs_per_batch=3)
     assert torch.equal(b[0], a[0]) and torch.equal(b[1], a[0])
+    c = eng.eval_sequences(two, Tm, reinit_period=500, frames_per_batch=24, pairs_per_batch=32)   # one SCoordNet batch, tower sub-batches 16 + 8
+    assert torch.equal(c[0], a[0]) and torch.equal(c[1], a[0])
 
 
 def test_host_buffer_entry_point_matches_device_path(staged):
