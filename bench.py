@@ -583,10 +583,10 @@ def main():
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--sequences", type=int, default=0,
                     help="total sequences of the job, sharded over the ranks (0 = default: 1 at N = 1, the fixed 8 of configs[4] at N > 1)")
-    ap.add_argument("--frames_per_batch", type=int, default=71,
-                    help="frames per SCoordNet batch.  The 60x80-grid layers have 37.5 M-tiles per frame; on 148 SMs a batch of 16 (600 tiles = 4.05 "
-                         "waves) leaves conv6 a 5th wave that is 5 %% full, conv5 and conv4b lose 10 %% / 5 %% the same way.  71 frames = 2662.5 tiles = "
-                         "17.99 waves (256 = 3 x 71 + 43, and 43 frames = 10.9 waves).  The tower runs in sub-batches of 16 inside each batch")
+    ap.add_argument("--frames_per_batch", type=int, default=32,
+                    help="frames per SCoordNet batch (the tower runs in sub-batches of 16 inside it).  Measured trade-off: larger batches fill the "
+                         "last wave of the 60x80-grid layers better (37.5 M-tiles per frame on 148 SMs), smaller ones keep the 9-tap re-reads of "
+                         "a layer's input in the 126 MB L2; 32 wins (profiles/r02h_ab_runs.txt, r02j_ab_runs.txt: 16 / 32 / 63 / 71 / 128)")
     ap.add_argument("--pairs_per_batch", type=int, default=32)
     ap.add_argument("--cpu_frames", type=int, default=6)
     ap.add_argument("--parity_frames", type=int, default=3, help="frames of the fp64-oracle error check in the parity_mode block (0 = skip)")
