@@ -80,6 +80,7 @@ struct __align__(8) TcParams {
   // every W limb that pairs with that A limb is a shifted-descriptor MMA on the resident weights
   int a_chunks, w_chunks, n_limbs_a, n_limbs_w;
   uint32_t term_mask[3];        // bit lw of term_mask[la]: the product (A limb la) x (W limb lw) is accumulated
+  int strided;                  // interleaved tile assignment (see TileIter)
   int x3_fused;                 // non-halo limb modes: one stage holds ALL limbs of A and W for a (tap, chunk) -- every product that uses a
                                 // tile reads it from the same stage (4 tile loads per 3 products in fp16x2 instead of 6)
   int f16;                      // limbs are fp16 (KFN_MODE_FP16X2): limb 1 holds the residual scaled by 2^11
@@ -106,19 +107,37 @@ struct __align__(8) TcParams {
 // incremental coordinate updates: the integer divisions of the decode happen once per CTA, not once per tile per
 // role (profiles/r01c: the per-tile div/mod + pointer arithmetic was ~1900 cycles on the epilogue's critical path).
 struct TileIter {
-  int tile, end, nt, tw, th, tn;
-  __device__ __forceinline__ void init(const TcParams& p, int total) {
-    const int base = total / (int)gridDim.x, rem = total % (int)gridDim.x, b = (int)blockIdx.x;
-    tile = b * base + (b < rem ? b : rem);
-    end = tile + base + (b < rem ? 1 : 0);
+  int tile, end, nt, tw, th, tn, step;
+  __device__ __forceinline__ void decode(const TcParams& p) {
     nt = tile % p.n_tiles;
     int mt = tile / p.n_tiles;
     tw = mt % p.tiles_w; mt /= p.tiles_w;
     th = mt % p.tiles_h;
     tn = mt / p.tiles_h;
   }
+  __device__ __forceinline__ void init(const TcParams& p, int total) {
+    if (p.strided) {
+      // interleaved assignment: CTA b walks tiles b, b + G, b + 2G, ...  At any moment the G CTAs of the grid work inside a window of
+      // G consecutive tiles (neighbouring pixels, all N tiles of the same pixels together), so a tile's halo and the operand tiles its
+      // neighbours need are fetched from DRAM once and hit in L2 for everyone else; with contiguous per-CTA ranges the grid touches
+      // 148 distant regions at once.  Costs a few integer divisions per tile: used for the layers whose tiles carry thousands of MMA cycles.
+      tile = (int)blockIdx.x; end = total; step = (int)gridDim.x;
+      if (tile < end) decode(p);
+      return;
+    }
+    const int base = total / (int)gridDim.x, rem = total % (int)gridDim.x, b = (int)blockIdx.x;
+    tile = b * base + (b < rem ? b : rem);
+    end = tile + base + (b < rem ? 1 : 0);
+    step = 1;
+    decode(p);
+  }
   __device__ __forceinline__ bool valid() const { return tile < end; }
   __device__ __forceinline__ void next(const TcParams& p) {
+    if (step != 1) {
+      tile += step;
+      if (tile < end) decode(p);
+      return;
+    }
     ++tile;
     if (++nt == p.n_tiles) { nt = 0; if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } } }
   }
@@ -1194,6 +1213,12 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   }
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   const int max_ctas = num_sms * plan->ctas_per_sm;
+  {
+    // big one-CTA layers only: >= 2000 tensor cycles per tile amortise the per-tile index decode
+    static const bool strided_on = env_flag("KFN_TC_STRIDED", true);
+    const int64_t tile_cycles = (int64_t)g.ntaps * (g.Cin / KC) * (KC / 16) * (BN / 2 > 48 ? BN / 2 : 48) * (p.n_terms > 0 ? p.n_terms : 1);
+    p.strided = (strided_on && plan->ctas_per_sm == 1 && !g.im2col_u8 && !g.diff_cur && tile_cycles >= 2000 && total_tiles > max_ctas) ? 1 : 0;
+  }
   plan->grid = total_tiles < max_ctas ? total_tiles : max_ctas;
   return KFN_OK;
 }
