@@ -81,6 +81,7 @@ struct __align__(8) TcParams {
   int a_chunks, w_chunks, n_limbs_a, n_limbs_w;
   uint32_t term_mask[3];        // bit lw of term_mask[la]: the product (A limb la) x (W limb lw) is accumulated
   int strided;                  // interleaved tile assignment (see TileIter)
+  int pair;                     // CTA-pair plan (conv_tc_kernel_pair): 256-row tiles, each CTA loads its 128 rows of A and 128 of the 256 rows of B
   int x3_fused;                 // non-halo limb modes: one stage holds ALL limbs of A and W for a (tap, chunk) -- every product that uses a
                                 // tile reads it from the same stage (4 tile loads per 3 products in fp16x2 instead of 6)
   int f16;                      // limbs are fp16 (KFN_MODE_FP16X2): limb 1 holds the residual scaled by 2^11
@@ -893,6 +894,202 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
   }
 }
 
+// ------------------------------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
+// The N = 256-column layers of SCoordNet (conv2a .. conv6).  Two CTAs of a cluster (neighbouring SMs) execute ONE tcgen05.mma of
+// M = 256 x N = 256: each CTA stages only ITS 128 rows of A and ITS 128 of the 256 rows of the weight tile (32 KB per k-block instead
+// of 48 KB), the tensor core of each SM reads both halves of B, each CTA's TMEM receives its own 128 rows of D.  What it buys: the
+// one-CTA kernel keeps 4 x 48 KB in flight against a consumption of 96 B/clk per SM -- the ncu capture of conv2b shows the MMA issuer
+// waiting for operands a quarter of the time, the producer waiting for a free stage 40 % of the time; here 6 x 32 KB are in flight
+// against 64 B/clk.  Leader = cluster rank 0: it alone issues the MMAs; every full barrier lives in the leader (both CTAs' TMA loads
+// complete on it), tcgen05.commit multicasts the stage-free / accumulator-ready arrivals to both CTAs, the epilogue warps of both
+// CTAs release the accumulator on the leader's barrier.
+struct PairIter {
+  int pt, end, step, nt, tw, th, tn;
+  __device__ __forceinline__ void decode(const TcParams& p, int rank) {
+    nt = pt % p.n_tiles;
+    int mt = (pt / p.n_tiles) * 2 + rank;          // this CTA's 128-row tile of the pair's 256 rows (may lie past the end: all rows invalid)
+    tw = mt % p.tiles_w; mt /= p.tiles_w;
+    th = mt % p.tiles_h;
+    tn = mt / p.tiles_h;
+  }
+  __device__ __forceinline__ void init(const TcParams& p, int total_pt, int rank) {
+    pt = (int)(blockIdx.x >> 1); end = total_pt; step = (int)(gridDim.x >> 1);
+    if (pt < end) decode(p, rank);
+  }
+  __device__ __forceinline__ bool valid() const { return pt < end; }
+  __device__ __forceinline__ void next(const TcParams& p, int rank) { pt += step; if (pt < end) decode(p, rank); }
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[kMaxStages];
+  __shared__ __align__(8) uint64_t s_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t s_tfull[2];
+  __shared__ __align__(8) uint64_t s_tempty[2];
+  __shared__ uint32_t s_tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&s_tfull[a]), 1); mbar_init(smem_u32(&s_tempty[a]), 2u * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {   // one warp of EACH CTA of the pair: the allocation is collective
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // the peer's barriers exist before anything is signalled on them
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_pt = ((m_tiles + 1) >> 1) * p.n_tiles;
+  const uint32_t b_half = p.b_bytes >> 1;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (one lane, both CTAs)
+    if (elect_one(lane)) {
+      int s = 0;
+      uint32_t ph = 0;
+      PairIter it;
+      for (it.init(p, total_pt, rank); it.valid(); it.next(p, rank)) {
+        const int w0 = it.tw << p.lbw, h0 = it.th << p.lbh, n0 = it.tn << (7 - p.lbw - p.lbh);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int dy = p.dy[tap], dx = p.dx[tap];
+          int cw, cpar, chh, coff;
+          if (p.istride == 1) { cw = w0 + dx; cpar = 0; chh = h0 + dy; coff = 0; }
+          else { cw = w0 + (dx >> 1); cpar = dy & 1; chh = h0 + (dy >> 1); coff = (dx & 1) * p.in_cs; }
+          for (int kc = 0; kc < p.cpk; ++kc) {
+            mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);                       // the pair's MMAs that read this stage (in BOTH CTAs) have retired
+            const uint32_t full_leader = mapa_cluster(smem_u32(&s_full[s]), 0u);
+            if (leader) mbar_expect_tx(smem_u32(&s_full[s]), 2u * (p.a_bytes + b_half));   // both CTAs' loads land on the leader's barrier
+            const uint32_t a_dst = smem_base + (uint32_t)s * p.stage_bytes;
+            tma_load_5d_2cta(a_dst, &tmA, full_leader, coff + kc * p.KC, cw, cpar, chh, n0);
+            tma_load_3d_2cta(a_dst + p.a_bytes, &tmB, full_leader, kc * p.KC, it.nt * p.BN + rank * (p.BN >> 1), tap);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one lane of the LEADER)
+    if (leader && elect_one(lane)) {
+      const uint64_t desc_fixed = ((uint64_t)p.desc_hi << 32) | (1ull << 16);
+      const uint64_t stage16 = (uint64_t)(p.stage_bytes >> 4);
+      const uint64_t a0 = desc_fixed | (uint64_t)(smem_base >> 4);
+      const uint64_t b_off = (uint64_t)(p.a_bytes >> 4);
+      const int kblocks = p.ntaps * p.cpk;
+      int s = 0, j = 0;
+      uint32_t ph = 0;
+      uint64_t adesc = a0;
+      PairIter it;
+      for (it.init(p, total_pt, rank); it.valid(); it.next(p, rank), ++j) {
+        const int a = j & 1;
+        mbar_wait(smem_u32(&s_tempty[a]), (((uint32_t)j >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)a * 256u;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(smem_u32(&s_full[s]), ph);
+          tc_fence_after();
+          umma_kblock_2cta<4>(tmem_d, adesc, adesc + b_off, p.idesc, kb ? 1u : 0u);
+          umma_commit_2cta(smem_u32(&s_empty[s]));
+          adesc += stage16;
+          if (++s == p.stages) { s = 0; ph ^= 1u; adesc = a0; }
+        }
+        umma_commit_2cta(smem_u32(&s_tfull[a]));
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (8 warps per CTA: own 128 rows, 256 columns)
+    const int quad = warp & 3, hsel = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    uint8_t* stg = smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_stage_off + (uint32_t)(warp - 2) * 2048u;
+    auto row_off = [&](int r, int& r_ni) -> int64_t {
+      const int r_wi = r & ((1 << p.lbw) - 1);
+      const int r_hi = (r >> p.lbw) & ((1 << p.lbh) - 1);
+      r_ni = r >> (p.lbw + p.lbh);
+      return (((int64_t)r_ni * p.OH + r_hi) * p.OW + r_wi) * p.out_cs * 2;
+    };
+    int64_t wr_off[4];
+    int wr_ni[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wr_off[i] = row_off(quad * 32 + i * 8 + (lane >> 2), wr_ni[i]);
+    (void)row;
+    const int sw_st = (lane >> 1) & 3, cq = lane & 3;
+    const uint32_t tempty_leader0 = mapa_cluster(smem_u32(&s_tempty[0]), 0u), tempty_leader1 = mapa_cluster(smem_u32(&s_tempty[1]), 0u);
+    int j = 0;
+    PairIter it;
+    for (it.init(p, total_pt, rank); it.valid(); it.next(p, rank), ++j) {
+      const int a = j & 1;
+      const int n0 = it.tn << (7 - p.lbw - p.lbh);
+      const int64_t tile_off = ((((int64_t)n0 * p.OH + (it.th << p.lbh)) * p.OW + (it.tw << p.lbw)) * p.out_cs + p.out_coff) * 2;
+      uint8_t* const tile_ptr = reinterpret_cast<uint8_t*>(p.out) + tile_off;
+      uint8_t* wrow[4];
+      bool wvalid[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { wrow[i] = tile_ptr + wr_off[i]; wvalid[i] = n0 + wr_ni[i] < p.N; }
+      mbar_wait(smem_u32(&s_tfull[a]), ((uint32_t)j >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)a * 256u;
+      const int col0 = it.nt * p.BN;
+      for (int nc = 0; nc < 256; nc += 32) {
+        if (((nc >> 5) & 1) != hsel) continue;
+        uint32_t r[32];
+        tmem_ld32(taddr + nc, r);
+        const int c = col0 + nc;
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bq = __ldg(b4 + q);
+          v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bq.x; v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq.y;
+          v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq.z; v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq.w;
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw_st) << 4)) =
+                make_uint4(pack_bf16_relu(v[8 * q + 0], v[8 * q + 1]), pack_bf16_relu(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16_relu(v[8 * q + 4], v[8 * q + 5]), pack_bf16_relu(v[8 * q + 6], v[8 * q + 7]));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw_st) << 4)) =
+                make_uint4(pack_bf16(v[8 * q + 0], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2);
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((cq ^ ((rr >> 1) & 3)) << 4));
+          if (wvalid[i]) *reinterpret_cast<uint4*>(wrow[i] + (int64_t)c * 2 + cq * 16) = val;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(a ? tempty_leader1 : tempty_leader0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // neither CTA leaves (or frees TMEM) while its peer may still read its shared memory / signal it
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
 // One CTA per SM for the big compute-bound layers; two co-resident CTAs per SM (half the smem budget, TMEM by need)
 // for the small latency-bound ones, so one CTA's barrier / TMA / TMEM latencies are covered by the other's work.
 __global__ void __launch_bounds__(kThreads, 1)
@@ -1166,6 +1363,17 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
       p.x3_fused = 1;
       p.stage_bytes = fused_stage;
     }
+    // CTA-pair plan (conv_tc_kernel_pair): plain bf16 layers with a 256-column tile and 64-channel chunks, on their own SM
+    static const bool pair_on = env_flag("KFN_TC_PAIR", false);   // opt-in until validated on hardware
+    const bool pair = pair_on && !x3 && !g.half_limbs && BN == 256 && KC == 64 && plan->ctas_per_sm == 1 && !wide && !g.im2col_u8 && !g.diff_cur &&
+                      out_bf16 && g.limbs_out <= 1 && g.phase_cout == 0 && g.epi == EPI_NONE && !out2 && g.omul == 1 && (num_sms & 1) == 0 &&
+                      ((g.out_cs * 2) & 15) == 0 && ((g.out_coff * 2) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                      (int64_t)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles >= 2 * (int64_t)num_sms;
+    if (pair) {
+      p.pair = 1;
+      p.stage_bytes = p.a_bytes + (p.b_bytes >> 1);          // 128 rows of A + this CTA's 128 of the 256 rows of B
+      p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // M = 256 across the pair
+    }
     uint32_t resident = 0;
     if (g.im2col_u8) {   // resident weight tile at the base, stages hold only the A tile the producer warps write
       p.im2col = 1; p.img = reinterpret_cast<const uint8_t*>(in);
@@ -1196,7 +1404,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   // ---- B: packed weights [tap][CoutP][Cin]
   cuuint64_t dimB[3] = {(cuuint64_t)g.Cin * limbs_w, (cuuint64_t)CoutP, (cuuint64_t)g.ntaps};
   cuuint64_t strB[2] = {(cuuint64_t)g.Cin * limbs_w * 2, (cuuint64_t)g.Cin * limbs_w * 2 * CoutP};
-  cuuint32_t boxB[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1u};
+  cuuint32_t boxB[3] = {(cuuint32_t)KC, (cuuint32_t)(p.pair ? BN / 2 : BN), 1u};
   r = encode(tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dimB, strB, boxB, ones,
              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); return KFN_ERR_CUDA; }
@@ -1220,6 +1428,14 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     p.strided = (strided_on && plan->ctas_per_sm == 1 && !g.im2col_u8 && !g.diff_cur && tile_cycles >= 2000 && total_tiles > max_ctas) ? 1 : 0;
   }
   plan->grid = total_tiles < max_ctas ? total_tiles : max_ctas;
+  plan->pair = p.pair;
+  if (p.pair) {
+    const int pair_tiles = ((p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2) * p.n_tiles;
+    const int pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
+    plan->grid = 2 * pairs;
+    plan->threads = kThreads;
+    p.strided = 0;
+  }
   return KFN_OK;
 }
 
@@ -1237,6 +1453,7 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_first, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_diff, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
   const CUtensorMap* tmA = reinterpret_cast<const CUtensorMap*>(plan.blob);
@@ -1252,7 +1469,15 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
-  if (p.diffp)
+  if (plan.pair) {
+    cudaLaunchAttribute attr2[2];
+    attr2[0].id = cudaLaunchAttributeClusterDimension;
+    attr2[0].val.clusterDim.x = 2; attr2[0].val.clusterDim.y = 1; attr2[0].val.clusterDim.z = 1;
+    attr2[1] = attr[0];
+    cfg.attrs = attr2;
+    cfg.numAttrs = tc_pdl_enabled() ? 2 : 1;
+    KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_pair, tmA[0], tmA[1], p));
+  } else if (p.diffp)
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_diff, tmA[0], tmA[1], p));
   else if (p.im2col)
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_first, tmA[0], tmA[1], p));

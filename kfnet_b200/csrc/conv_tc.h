@@ -11,6 +11,7 @@ struct TcConvPlan {
   int ctas_per_sm;
   int threads;                    // 320, 192 (three CTAs per SM) or 576 (WIDE)
   int lean;                       // plain bf16 layer: co-resident plans use the lean kernel body
+  int pair;                       // CTA-pair plan: conv_tc_kernel_pair, launched as clusters of 2
   size_t smem;
 };
 
