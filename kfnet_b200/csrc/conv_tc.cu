@@ -1364,7 +1364,7 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
       p.stage_bytes = fused_stage;
     }
     // CTA-pair plan (conv_tc_kernel_pair): plain bf16 layers with a 256-column tile and 64-channel chunks, on their own SM
-    static const bool pair_on = env_flag("KFN_TC_PAIR", false);   // opt-in until validated on hardware
+    static const bool pair_on = env_flag("KFN_TC_PAIR", true);    // KFN_TC_PAIR=0: one-CTA tiles (A/B measurements)
     const bool pair = pair_on && !x3 && !g.half_limbs && BN == 256 && KC == 64 && plan->ctas_per_sm == 1 && !wide && !g.im2col_u8 && !g.diff_cur &&
                       out_bf16 && g.limbs_out <= 1 && g.phase_cout == 0 && g.epi == EPI_NONE && !out2 && g.omul == 1 && (num_sms & 1) == 0 &&
                       ((g.out_cs * 2) & 15) == 0 && ((g.out_coff * 2) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&

@@ -191,3 +191,22 @@ def test_fused_conv1ab(engines, weights, shape):
     ref = _ref_layer(weights, "ScoreNet/conv1b", "conv", mid.float(), 1, True, True)
     assert_close_rms(fused.float(), ref, 1e-2, "fused conv1ab vs fp32 reference")
 
+
+
+@pytest.mark.skipif(not feature_on("KFN_TC_PAIR"), reason="CTA-pair tiles switched off (KFN_TC_PAIR=0)")
+@pytest.mark.parametrize("key,cin,cout,stride,N,OH,OW", [
+    ("ScoreNet/conv2b", 256, 256, 1, 5, 120, 168),      # 945 M-tiles: odd -> the last pair has a phantom half; ragged batch (bn = 2, N = 5)
+    ("ScoreNet/conv3a", 256, 512, 2, 5, 120, 168),      # stride-2 parity view, two N tiles
+    ("ScoreNet/conv6", 512, 256, 1, 16, 60, 80),        # the 60x80 grid at batch 16: 600 M-tiles, 4.05 waves of pairs
+])
+def test_cta_pair_layers(engines, weights, key, cin, cout, stride, N, OH, OW):
+    """conv_tc_kernel_pair (tcgen05.mma.cta_group::2, 256-row tiles): layers large enough to take the pair plan (>= 2 tiles per SM) vs a
+    PyTorch fp32 conv of the same bf16 operands: one bf16 ulp."""
+    g = torch.Generator().manual_seed(zlib.crc32(key.encode()) % 1000 + 7)
+    x = (torch.randn(N, OH * stride, OW * stride, cin, generator=g) * 0.5).cuda().to(torch.bfloat16)
+    ref = _ref_layer(weights, key, "conv", x.float(), stride, True, True)
+    got = engines["bf16"].conv_layer(key, x.contiguous(), (OH, OW), cout)
+    assert_close_rms(got.float(), ref, BF16_ULP, key + " CTA-pair tiles, bf16 out")
+    out = torch.full((N, OH, OW, cout + 64), 3.0, dtype=torch.bfloat16, device="cuda")          # channel offset inside a wider buffer
+    engines["bf16"].conv_layer(key, x.contiguous(), (OH, OW), cout + 64, out_coff=32, out=out)
+    assert torch.equal(out[..., 32:32 + cout], got) and bool((out[..., :32] == 3.0).all()) and bool((out[..., 32 + cout:] == 3.0).all())

@@ -33,7 +33,7 @@ def rel_err_quantile(a, b, q):
 
 # kernel variants behind env switches (kfnet_b200/csrc/conv_tc.cu env_flag defaults); a variant that is opt-in has its
 # dedicated tests skipped when it is switched off, so the suite always describes the code path that actually runs
-FEATURE_DEFAULTS = {"KFN_TC_WIDE": True, "KFN_TC_IM2COL_FUSED": True, "KFN_TC_GROUP2": True, "KFN_TC_FUSE_CONV1": False}
+FEATURE_DEFAULTS = {"KFN_TC_WIDE": True, "KFN_TC_IM2COL_FUSED": True, "KFN_TC_GROUP2": True, "KFN_TC_FUSE_CONV1": False, "KFN_TC_PAIR": True}
 
 
 def feature_on(name):
