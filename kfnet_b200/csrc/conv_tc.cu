@@ -974,10 +974,20 @@ conv_tc_kernel_pair(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int kc = 0; kc < p.cpk; ++kc) {
             mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);                       // the pair's MMAs that read this stage (in BOTH CTAs) have retired
             const uint32_t full_leader = mapa_cluster(smem_u32(&s_full[s]), 0u);
-            if (leader) mbar_expect_tx(smem_u32(&s_full[s]), 2u * (p.a_bytes + b_half));   // both CTAs' loads land on the leader's barrier
             const uint32_t a_dst = smem_base + (uint32_t)s * p.stage_bytes;
-            tma_load_5d_2cta(a_dst, &tmA, full_leader, coff + kc * p.KC, cw, cpar, chh, n0);
-            tma_load_3d_2cta(a_dst + p.a_bytes, &tmB, full_leader, kc * p.KC, it.nt * p.BN + rank * (p.BN >> 1), tap);
+            if (p.x3acc) {
+              // limb modes: the stage holds every limb of this CTA's A rows and of its half of the weight tile (fused-limb stage)
+              if (leader) mbar_expect_tx(smem_u32(&s_full[s]), 2u * ((uint32_t)p.n_limbs_a * p.a_bytes + (uint32_t)p.n_limbs_w * b_half));
+              for (int la = 0; la < p.n_limbs_a; ++la)
+                tma_load_5d_2cta(a_dst + (uint32_t)la * p.a_bytes, &tmA, full_leader, coff + la * p.in_ls + kc * p.KC, cw, cpar, chh, n0);
+              for (int lw = 0; lw < p.n_limbs_w; ++lw)
+                tma_load_3d_2cta(a_dst + (uint32_t)p.n_limbs_a * p.a_bytes + (uint32_t)lw * b_half, &tmB, full_leader, lw * p.w_cin + kc * p.KC,
+                                 it.nt * p.BN + rank * (p.BN >> 1), tap);
+            } else {
+              if (leader) mbar_expect_tx(smem_u32(&s_full[s]), 2u * (p.a_bytes + b_half));   // both CTAs' loads land on the leader's barrier
+              tma_load_5d_2cta(a_dst, &tmA, full_leader, coff + kc * p.KC, cw, cpar, chh, n0);
+              tma_load_3d_2cta(a_dst + p.a_bytes, &tmB, full_leader, kc * p.KC, it.nt * p.BN + rank * (p.BN >> 1), tap);
+            }
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
@@ -995,6 +1005,32 @@ conv_tc_kernel_pair(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t ph = 0;
       uint64_t adesc = a0;
       PairIter it;
+      if (p.x3acc) {
+        // limb modes: four 128-column accumulators (main term round-robin by tap over 0..2, correction terms in 3), single-buffered
+        const uint64_t a16 = (uint64_t)(p.a_bytes >> 4), bh16 = (uint64_t)(b_half >> 4);
+        const uint64_t w_off = (uint64_t)p.n_limbs_a * a16;
+        for (it.init(p, total_pt, rank); it.valid(); it.next(p, rank), ++j) {
+          mbar_wait(smem_u32(&s_tempty[0]), ((uint32_t)j & 1u) ^ 1u);
+          tc_fence_after();
+          uint32_t used = 0;
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            for (int kc = 0; kc < p.cpk; ++kc) {
+              mbar_wait(smem_u32(&s_full[s]), ph);
+              tc_fence_after();
+              for (int t = 0; t < p.n_terms; ++t) {
+                const int acc = (p.la[t] == 0 && p.lw[t] == 0) ? (tap % 3) : 3;
+                umma_kblock_2cta<4>(tmem_base + (uint32_t)acc * p.acc_stride, adesc + (uint64_t)p.la[t] * a16, adesc + w_off + (uint64_t)p.lw[t] * bh16,
+                                    p.idesc, (used >> acc) & 1u);
+                used |= 1u << acc;
+              }
+              umma_commit_2cta(smem_u32(&s_empty[s]));
+              adesc += stage16;
+              if (++s == p.stages) { s = 0; ph ^= 1u; adesc = a0; }
+            }
+          }
+          umma_commit_2cta(smem_u32(&s_tfull[0]));
+        }
+      } else
       for (it.init(p, total_pt, rank); it.valid(); it.next(p, rank), ++j) {
         const int a = j & 1;
         mbar_wait(smem_u32(&s_tempty[a]), (((uint32_t)j >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator
@@ -1031,6 +1067,73 @@ conv_tc_kernel_pair(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t tempty_leader0 = mapa_cluster(smem_u32(&s_tempty[0]), 0u), tempty_leader1 = mapa_cluster(smem_u32(&s_tempty[1]), 0u);
     int j = 0;
     PairIter it;
+    if (p.x3acc) {
+      // limb modes: BN = 128 columns per tile, two warps per lane quadrant split the four 32-column blocks; the accumulators are added with
+      // round-to-nearest fp32 (the correction accumulator scaled by corr_scale), then split back into limbs
+      const bool f16 = p.f16 != 0;
+      const int n_main = p.ntaps < 3 ? p.ntaps : 3;
+      for (it.init(p, total_pt, rank); it.valid(); it.next(p, rank), ++j) {
+        const int n0 = it.tn << (7 - p.lbw - p.lbh);
+        const int64_t tile_off = ((((int64_t)n0 * p.OH + (it.th << p.lbh)) * p.OW + (it.tw << p.lbw)) * p.out_cs + p.out_coff) * 2;
+        uint8_t* const tile_ptr = reinterpret_cast<uint8_t*>(p.out) + tile_off;
+        uint8_t* wrow[4];
+        bool wvalid[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { wrow[i] = tile_ptr + wr_off[i]; wvalid[i] = n0 + wr_ni[i] < p.N; }
+        mbar_wait(smem_u32(&s_tfull[0]), (uint32_t)j & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int col0 = it.nt * p.BN;
+        for (int nc = 0; nc < p.BN; nc += 32) {
+          if (((nc >> 5) & 1) != hsel) continue;
+          uint32_t r[32];
+          tmem_ld32(taddr + nc, r);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          for (int acc = 1; acc < 4; ++acc) {
+            if (acc < 3 && acc >= n_main) continue;
+            tmem_ld32(taddr + (uint32_t)acc * p.acc_stride + nc, r);
+            const float sc = acc == 3 ? p.corr_scale : 1.0f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), sc, v[i]);
+          }
+          const int c = col0 + nc;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = __ldg(b4 + q);
+            v[4 * q + 0] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          for (int l = 0; l < p.out_limbs; ++l) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw_st) << 4)) =
+                  make_uint4(pack_limb(v[8 * q + 0], v[8 * q + 1], f16), pack_limb(v[8 * q + 2], v[8 * q + 3], f16),
+                             pack_limb(v[8 * q + 4], v[8 * q + 5], f16), pack_limb(v[8 * q + 6], v[8 * q + 7], f16));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + (lane >> 2);
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((cq ^ ((rr >> 1) & 3)) << 4));
+              if (wvalid[i]) *reinterpret_cast<uint4*>(wrow[i] + ((int64_t)c + (int64_t)l * p.out_ls) * 2 + cq * 16) = val;
+            }
+            __syncwarp();
+            if (l + 1 < p.out_limbs) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = limb_residual(v[i], f16);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader0);
+      }
+    } else
     for (it.init(p, total_pt, rank); it.valid(); it.next(p, rank), ++j) {
       const int a = j & 1;
       const int n0 = it.tn << (7 - p.lbw - p.lbh);
@@ -1365,14 +1468,21 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     }
     // CTA-pair plan (conv_tc_kernel_pair): plain bf16 layers with a 256-column tile and 64-channel chunks, on their own SM
     static const bool pair_on = env_flag("KFN_TC_PAIR", true);    // KFN_TC_PAIR=0: one-CTA tiles (A/B measurements)
-    const bool pair = pair_on && !x3 && !g.half_limbs && BN == 256 && KC == 64 && plan->ctas_per_sm == 1 && !wide && !g.im2col_u8 && !g.diff_cur &&
-                      out_bf16 && g.limbs_out <= 1 && g.phase_cout == 0 && g.epi == EPI_NONE && !out2 && g.omul == 1 && (num_sms & 1) == 0 &&
-                      ((g.out_cs * 2) & 15) == 0 && ((g.out_coff * 2) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                      (int64_t)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles >= 2 * (int64_t)num_sms;
-    if (pair) {
+    static const bool pair_x3_on = env_flag("KFN_TC_PAIR_X3", true);   // the limb modes' pair plan (A/B switch)
+    const bool pair_common = pair_on && KC == 64 && plan->ctas_per_sm == 1 && !wide && !g.im2col_u8 && !g.diff_cur && out_bf16 && g.phase_cout == 0 &&
+                             g.epi == EPI_NONE && !out2 && g.omul == 1 && (num_sms & 1) == 0 && ((g.out_cs * 2) & 15) == 0 &&
+                             ((g.out_coff * 2) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                             (int64_t)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles >= 2 * (int64_t)num_sms;
+    const uint32_t pair_x3_stage = (uint32_t)limbs_a * p.a_bytes + (uint32_t)limbs_w * (p.b_bytes >> 1);
+    const bool pair = pair_common && !x3 && !g.half_limbs && BN == 256 && g.limbs_out <= 1;
+    const bool pair_x3 = pair_common && pair_x3_on && x3 && BN == 128 && ((p.out_ls * 2) & 15) == 0 && 2u * pair_x3_stage <= budget;
+    if (pair || pair_x3) {
       p.pair = 1;
-      p.stage_bytes = p.a_bytes + (p.b_bytes >> 1);          // 128 rows of A + this CTA's 128 of the 256 rows of B
-      p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // M = 256 across the pair
+      p.x3_fused = 0;
+      // 128 rows of A + this CTA's half of the weight tile (every limb of both in the limb modes)
+      p.stage_bytes = pair_x3 ? pair_x3_stage : p.a_bytes + (p.b_bytes >> 1);
+      const uint32_t ab_fmt2 = g.half_limbs ? 0u : 1u;
+      p.idesc = (1u << 4) | (ab_fmt2 << 7) | (ab_fmt2 << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // M = 256 across the pair
     }
     uint32_t resident = 0;
     if (g.im2col_u8) {   // resident weight tile at the base, stages hold only the A tile the producer warps write
