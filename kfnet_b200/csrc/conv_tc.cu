@@ -92,6 +92,8 @@ struct __align__(8) TcParams {
   // 0.00625 scale is folded into the packed weights; taps outside the image are 0 = SAME padding of the preprocessed
   // tensor); the [BN x 32] weight tile is resident.  No im2col tensor ever exists in HBM.
   int im2col;
+  int ph16;                     // merged deconv with four 16-channel phases: one-wait epilogue (upconv0)
+  int par_issue;                // > 0: warp-parallel TMA issue, this many k-blocks (lanes) per pass (<= stages)
   const uint8_t* img;
   uint32_t tap_off16[9];        // halo: ((1+dy) * 10*bn + (1+dx)) * row_bytes / 16 per tap
   // fused difference volume (U-Net conv0, BF16 mode): the halo tile's rows are diff[p,i,j,:] = f_cur[p,:] - f_prev[p + (j-4, i-4),:]
@@ -352,12 +354,12 @@ __device__ __forceinline__ void mma_role_halo_x3(const TcParams& p, uint32_t sme
 // kLean (WIDE / fused-first-layer kernels): plain bf16 layers only -- the bf16x3 accumulator splits, limb outputs,
 // conv2d_transpose phase scatter and special epilogues are compiled out, which shortens the per-tile epilogue chain
 // these layers are bound by and frees registers for the 576 / 672-thread CTAs.
-template <bool kLean, int kProd>
+template <bool kLean, int kProd, bool kPh16 = false>
 __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
   const int f_x3acc = kLean ? 0 : p.x3acc;
   const int f_out_limbs = kLean ? 1 : p.out_limbs;
   const int f_out_ls = kLean ? 0 : p.out_ls;
-  const int f_phase_cout = kLean ? 0 : p.phase_cout;
+  const int f_phase_cout = kProd != 0 ? 0 : p.phase_cout;   // merged conv2d_transpose phases (in the lean body too, not in the producer-warp kernels)
   const int f_epi = kLean ? (int)EPI_NONE : p.epi;
   const bool f_f16 = kLean ? false : (p.f16 != 0);
   const float f_cs = kLean ? 1.0f : p.corr_scale;
@@ -571,6 +573,55 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
+    } else if (!p.halo && p.par_issue) {
+      // ------------------------------------------------------------- warp-parallel issue (small-K-block layers)
+      // One elected lane walking the k-blocks spends ~70 dependent instructions (coordinate arithmetic, barrier wait, expect_tx, two
+      // TMA instructions) = 550-650 cycles on EACH k-block; for the 8-10 KB k-blocks of the U-Net / tower layers that chain, not the
+      // copy engine or the tensor core, was the layer's clock (ncu source view, profiles/r02s: the MMA lane waits for operands, the
+      // producer lane never waits for a free stage, the epilogue warps idle on the accumulator barrier half of the time).  Here lane l
+      // of a pass owns k-block base + l: up to `par_issue` (<= stages) k-blocks are issued by one pass through the same chain.  Lanes
+      // of one pass wait on DISTINCT stages whose previous fills were issued by earlier passes, so no lane's wait depends on
+      // another lane of the pass leaving its wait loop.
+      const int G = p.par_issue;
+      const int kpt = p.ntaps * p.cpk;                    // k-blocks per tile: (tap, chunk); a fused-limb stage holds every limb
+      int s0 = 0;
+      uint32_t ph0 = 0;
+      TileIter it;
+      for (it.init(p, total_tiles); it.valid(); it.next(p)) {
+        const int nt = it.nt;
+        const int w0 = it.tw << p.lbw, h0 = it.th << p.lbh, n0 = it.tn << (7 - p.lbw - p.lbh);
+        for (int base = 0; base < kpt; base += G) {
+          const int n = kpt - base < G ? kpt - base : G;
+          if (lane < n) {
+            const int kb = base + lane;
+            const int tap = kb / p.cpk, kc = kb - tap * p.cpk;
+            int s = s0 + lane;
+            uint32_t ph = ph0;
+            if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
+            const int dy = p.dy[tap], dx = p.dx[tap];
+            int cw, cpar, chh, coff;
+            if (p.istride == 1) { cw = w0 + dx; cpar = 0; chh = h0 + dy; coff = 0; }
+            else { cw = w0 + (dx >> 1); cpar = dy & 1; chh = h0 + (dy >> 1); coff = (dx & 1) * p.in_cs; }
+            mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);
+            const uint32_t full = smem_u32(&s_full[s]);
+            const uint32_t dst = smem_base + (uint32_t)s * p.stage_bytes;
+            if (p.x3_fused) {
+              mbar_expect_tx(full, (uint32_t)p.n_limbs_a * p.a_bytes + (uint32_t)p.n_limbs_w * p.b_bytes);
+              for (int la = 0; la < p.n_limbs_a; ++la)
+                tma_load_5d(dst + (uint32_t)la * p.a_bytes, &tmA, full, coff + la * p.in_ls + kc * p.KC, cw, cpar, chh, n0);
+              for (int lw = 0; lw < p.n_limbs_w; ++lw)
+                tma_load_3d(dst + (uint32_t)p.n_limbs_a * p.a_bytes + (uint32_t)lw * p.b_bytes, &tmB, full, lw * p.w_cin + kc * p.KC, nt * p.BN, tap);
+            } else {
+              mbar_expect_tx(full, p.a_bytes + p.b_bytes);
+              tma_load_5d(dst, &tmA, full, coff + kc * p.KC, cw, cpar, chh, n0);
+              tma_load_3d(dst + p.a_bytes, &tmB, full, kc * p.KC, nt * p.BN, tap);
+            }
+          }
+          __syncwarp();
+          s0 += n;
+          if (s0 >= p.stages) { s0 -= p.stages; ph0 ^= 1u; }
+        }
+      }
     } else if (producer_lane) {
       int s = 0;
       uint32_t ph = 0;
@@ -736,13 +787,52 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
         }
       } else {
         int nc = 0;
-        if (fast32) {
+        // merged conv2d_transpose: running (phase, channel-in-phase) of the current column block -- a runtime division per block
+        // sat on the epilogue's dependent chain (upconv0: four 16-column blocks per tile)
+        int ph_c = 0, cc_c = 0;
+        if (f_phase_cout && col0) { ph_c = col0 / f_phase_cout; cc_c = col0 - ph_c * f_phase_cout; }
+        auto adv_phase = [&](int wdt) {
+          if (f_phase_cout) { cc_c += wdt; if (cc_c >= f_phase_cout) { cc_c -= f_phase_cout; ++ph_c; } }
+        };
+        if (kPh16 && p.ph16) {
+          // merged conv2d_transpose with four 16-channel phases (U-Net upconv0, N = 64): both TMEM loads, ONE wait, then per phase
+          // bias + ReLU on the conversion + 32 contiguous bytes to pixel (2y + py, 2x + px).  The generic 16-column loop paid a TMEM
+          // round trip, a division and a parameter reload per phase: ~2300 cycles x 4 per tile, the layer's clock (profiles/r02s)
+          uint32_t ra[32], rb[32];
+          tmem_ld32_nowait(taddr, ra);
+          tmem_ld32_nowait(taddr + 32, rb);
+          tmem_wait_ld2(ra, rb);
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias);
+          const int64_t px_b = (int64_t)p.out_cs * 2, py_b = (int64_t)p.OW * p.out_cs * 2;
+#pragma unroll
+          for (int ph = 0; ph < 4; ++ph) {
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 bq = __ldg(b4 + ph * 4 + q);
+              const uint32_t* r = ph < 2 ? ra : rb;
+              const int o = (ph & 1) * 16 + 4 * q;
+              v[4 * q + 0] = __uint_as_float(r[o + 0]) + bq.x; v[4 * q + 1] = __uint_as_float(r[o + 1]) + bq.y;
+              v[4 * q + 2] = __uint_as_float(r[o + 2]) + bq.z; v[4 * q + 3] = __uint_as_float(r[o + 3]) + bq.w;
+            }
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = p.relu ? pack_bf16_relu(v[2 * i], v[2 * i + 1]) : pack_bf16(v[2 * i], v[2 * i + 1]);
+            if (valid) {
+              uint4* dst = reinterpret_cast<uint4*>(orow + (ph >> 1) * py_b + (ph & 1) * px_b);
+              dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+          }
+          nc = p.BN;
+        }
+        if (fast32 && !(kPh16 && p.ph16)) {
           uint8_t* wrow[4];
           bool wvalid[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) { wrow[i] = tile_ptr + wr_off[i]; wvalid[i] = n0 + wr_ni[i] < p.N; }
           const int fast_end = p.split_col ? p.split_col : p.Cout;
-          for (; nc + 32 <= p.BN && col0 + nc + 32 <= fast_end && (f_phase_cout == 0 || (f_phase_cout & 31) == 0); nc += 32) {
+          for (; nc + 32 <= p.BN && col0 + nc + 32 <= fast_end && (f_phase_cout == 0 || (f_phase_cout & 31) == 0); nc += 32, adv_phase(32)) {
             if (col_split && ((nc >> 5) & 1) != hsel) continue;
             uint32_t r[32];
             tmem_ld32(taddr + nc, r);
@@ -751,10 +841,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
             // merged conv2d_transpose: this 32-column block belongs to phase ph -> pixel offset (py, px), channel cc
             int cc = c;
             int64_t ph_off = 0;
-            if (!kLean && f_phase_cout) {
-              const int ph = c / (kLean ? 1 : f_phase_cout);
-              cc = c - ph * f_phase_cout;
-              ph_off = ((int64_t)(ph >> 1) * p.OW + (ph & 1)) * p.out_cs * 2;
+            if (f_phase_cout) {
+              cc = cc_c;
+              ph_off = ((int64_t)(ph_c >> 1) * p.OW + (ph_c & 1)) * p.out_cs * 2;
             }
             float v[32];
 #pragma unroll
@@ -811,7 +900,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
             }
           }
         }
-        for (; nc < p.BN; nc += 16) {
+        for (; nc < p.BN; nc += 16, adv_phase(16)) {
           if (col_split && ((nc >> 4) & 1) != hsel) continue;
           float v[16];
           tmem_ld16(taddr + nc, v);
@@ -841,10 +930,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
           const int nvalid = p.Cout - c;
           int cc = c;
           int64_t ph_off = 0;
-          if (!kLean && f_phase_cout) {
-            const int ph = c / (kLean ? 1 : f_phase_cout);
-            cc = c - ph * f_phase_cout;
-            ph_off = ((int64_t)(ph >> 1) * p.OW + (ph & 1)) * p.out_cs * esize;
+          if (f_phase_cout) {
+            cc = cc_c;
+            ph_off = ((int64_t)(ph_c >> 1) * p.OW + (ph_c & 1)) * p.out_cs * esize;
           }
           if (p.out_bf16) {
             uint8_t* rowbase = orow;
@@ -1208,6 +1296,12 @@ __global__ void __launch_bounds__(kThreads, 2)
 conv_tc_kernel_x2_lean(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   conv_tc_body<true, 0>(tmA, tmB, p);
 }
+// the same with the one-wait epilogue of the 4 x 16-channel merged deconv (U-Net upconv0) compiled in: its 64 live accumulator
+// registers would cost the other lean kernels spills
+__global__ void __launch_bounds__(kThreads, 2)
+conv_tc_kernel_x2_lean_ph(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  conv_tc_body<true, 0, true>(tmA, tmB, p);
+}
 // WIDE: 16 epilogue warps (four groups draining four tiles concurrently) for one-CTA layers with short tiles.
 __global__ void __launch_bounds__(kThreadsWide, 1)
 conv_tc_kernel_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -1406,14 +1500,18 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
   // bound it (tensor time per MMA ~ max(BN/2, 48) cycles: N <= 64 is bound by the A-operand fetch from smem).
   // Four accumulator stages of roundup(BN, 32) columns, four epilogue groups, 32 KB of store staging.
   const int64_t mma_cycles = (int64_t)g.ntaps * (g.Cin / KC) * (KC / 16) * (BN / 2 > 48 ? BN / 2 : 48);
-  const bool lean_ok = !x3 && !g.half_limbs && g.limbs_out <= 1 && g.phase_cout == 0 && g.epi == EPI_NONE;   // what conv_tc_body<true> keeps
+  const bool lean_ok = !x3 && !g.half_limbs && g.limbs_out <= 1 && g.epi == EPI_NONE;   // what conv_tc_body<true> keeps
+  if (g.im2col_u8 || g.diff_cur) KFN_REQUIRE(g.phase_cout == 0, "producer-warp kernels: no conv2d_transpose phases");
   if (g.im2col_u8) KFN_REQUIRE(lean_ok && plan->ctas_per_sm == 1, "fused first layer: plain bf16 layer, one CTA per SM");
   if (g.diff_cur) KFN_REQUIRE(lean_ok && plan->ctas_per_sm == 1 && halo && hbn == 2 && KC == 32, "fused difference volume: halo-tile plan");
-  const bool wide = tc_wide_enabled() && lean_ok && plan->ctas_per_sm == 1 && BN <= 128 && mma_cycles <= 2500 &&
+  const bool wide = tc_wide_enabled() && lean_ok && g.phase_cout == 0 && plan->ctas_per_sm == 1 && BN <= 128 && mma_cycles <= 2500 &&
                     (int64_t)g.N * g.MH * g.MW >= (int64_t)kBlockM * 8 * num_sms;
   p.lg_groups = -1; p.lg_acc = 1;
   plan->threads = plan->ctas_per_sm == 3 ? 192 : kThreads;
   plan->lean = (lean_ok && tc_lean_x2_enabled()) ? 1 : 0;
+  static const bool ph16_on = env_flag("KFN_TC_PH16", true);   // A/B switch: one-wait epilogue of the 4 x 16-channel deconv
+  p.ph16 = (ph16_on && plan->lean && plan->ctas_per_sm >= 2 && !wide && g.phase_cout == 16 && CoutP == 64 && g.Cout == 64 && out_bf16 &&
+            !out2 && ((g.out_cs * 2) & 15) == 0 && ((g.out_coff * 2) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
   if (wide) {
     p.lg_groups = 2; p.lg_acc = 2; p.epi_warps = 16;
     p.acc_stride = (uint32_t)(BN + 31) & ~31u;
@@ -1529,6 +1627,16 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
     if (dist < 2) dist = 2;
     p.pf_dist = (tc_prefetch_enabled() && (halo || kblocks <= 18)) ? dist : 0;
   }
+  {
+    // warp-parallel TMA issue for layers whose k-blocks are small and many per tile (see the producer): plain bf16 and fused-limb stages.
+    // Measured per layer (profiles/r02t): 8-9 lanes per pass: feat2 -32 %, U-Net conv1b -20 %, conv1a / conv2a / feat4 -11..13 %;
+    // 3-4 lanes per pass (24 KB stages, 3-4 of them): conv4 +23 %, conv2b +14 %, conv5 +6 % -- the pass costs about two serial k-blocks
+    static const bool par_on = env_flag("KFN_TC_PAR_ISSUE", true);
+    const int kpt = g.ntaps * p.cpk;
+    int G = p.stages < 32 ? p.stages : 32;
+    if (kpt < G) G = kpt;
+    p.par_issue = (par_on && !halo && !g.im2col_u8 && !g.diff_cur && !p.pair && p.pf_dist == 0 && (p.n_terms == 1 || p.x3_fused) && G >= 8) ? G : 0;
+  }
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   const int max_ctas = num_sms * plan->ctas_per_sm;
   {
@@ -1559,6 +1667,7 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, 106 * 1024));
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_x2_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, 106 * 1024));
+    KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_x2_lean_ph, cudaFuncAttributeMaxDynamicSharedMemorySize, 106 * 1024));
     // WIDE: 184 KB pipeline + 32 KB staging + 1 KB alignment; first layer in the 320-thread layout: 200 + 16 + 1 KB
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     KFN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel_first, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
@@ -1593,6 +1702,8 @@ int launch_conv_tc(const TcConvPlan& plan, cudaStream_t st) {
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_first, tmA[0], tmA[1], p));
   else if (plan.threads == kThreadsWide)
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_wide, tmA[0], tmA[1], p));
+  else if (plan.ctas_per_sm >= 2 && plan.lean && p.ph16)
+    KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_x2_lean_ph, tmA[0], tmA[1], p));
   else if (plan.ctas_per_sm >= 2 && plan.lean)
     KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel_x2_lean, tmA[0], tmA[1], p));
   else if (plan.ctas_per_sm >= 2)
