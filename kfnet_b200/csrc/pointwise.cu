@@ -362,14 +362,14 @@ kalman_scan_kernel(const float4* __restrict__ measure, const float2* __restrict_
 }
 
 // Cluster variant: the single-CTA scan above is instruction-issue bound on its one SM (~180 instructions per pixel),
-// so a sequence is spread over a thread-block cluster of kScanCluster CTAs.  Each CTA owns a band of label-grid rows
+// so a sequence is spread over a thread-block cluster of scan_cluster_size() CTAs.  Each CTA owns a band of label-grid rows
 // and keeps that band's state (double-buffered) in its own shared memory; the bilinear taps of the warp read whichever
 // CTA owns the sampled row through distributed shared memory (cluster.map_shared_rank), and one cluster.sync() per
 // frame replaces the __syncthreads().  Same arithmetic, same order: results are bit-identical to the single-CTA kernel.
 namespace cg = cooperative_groups;
-constexpr int kScanCluster = 4;
+constexpr int kScanClusterMax = 8;              // portable cluster limit; the size itself is a launch attribute (scan_cluster_size)
 
-__global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(1024, 1)
 kalman_scan_cluster_kernel(const float4* __restrict__ measure, const float2* __restrict__ flow, const float* __restrict__ sigma_w,
                            const float4* __restrict__ state_in, float4* __restrict__ state_out, Xform X, int T, int GH, int GW,
                            int first_index, int reinit_period, int nis_gate, float4* __restrict__ out_map,
@@ -377,17 +377,15 @@ kalman_scan_cluster_kernel(const float4* __restrict__ measure, const float2* __r
   extern __shared__ float4 s_band[];           // [2][cap]  this CTA's rows of the state
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int s = blockIdx.x / kScanCluster;
+  const int csize = (int)cluster.num_blocks();
+  const int s = blockIdx.x / csize;
   const int P = GH * GW;
-  const int rows_per = (GH + kScanCluster - 1) / kScanCluster;
+  const int rows_per = (GH + csize - 1) / csize;
   const int cap = rows_per * GW;
   const int y_lo = rank * rows_per;
   const int y_hi = min(GH, y_lo + rows_per);
   const int nloc = max(0, y_hi - y_lo) * GW;   // pixels owned by this CTA
   const int p_lo = y_lo * GW;
-  const float4* band[kScanCluster];            // every CTA's band, through distributed shared memory
-#pragma unroll
-  for (int r = 0; r < kScanCluster; ++r) band[r] = cluster.map_shared_rank(s_band, r);
   const int64_t seq = (int64_t)s * T * P;
   int cur = 0;
   if (state_in) {
@@ -398,9 +396,19 @@ kalman_scan_cluster_kernel(const float4* __restrict__ measure, const float2* __r
   const float minvar = 1e-5f * 1e-5f;
   const bool need_nis = (nis != nullptr) || (nis_gate != 0);
   auto gather = [&](int iy, int ix) -> float4 {
-    const int r = iy / rows_per;
-    return band[r][cur * cap + (iy - r * rows_per) * GW + ix];
+    const int r = iy / rows_per;                // owner of the sampled row: its band through distributed shared memory (mapa)
+    return cluster.map_shared_rank(s_band, r)[cur * cap + (iy - r * rows_per) * GW + ix];
   };
+  // inputs of this thread's first pixel of the NEXT frame are loaded while the current frame is still being computed and the
+  // cluster synchronises: the L2 round trip of the three loads leaves the per-frame critical path
+  float4 z_n = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 fl_n = make_float2(0.f, 0.f);
+  float sw_n = 0.f;
+  const bool own_first = (int)threadIdx.x < nloc;
+  if (own_first && T > 0) {
+    const int64_t q = seq + p_lo + threadIdx.x;
+    z_n = measure[q]; fl_n = flow[q]; sw_n = sigma_w[q];
+  }
   for (int t = 0; t < T; ++t) {
     const int64_t fr = seq + (int64_t)t * P;
     const int idx = first_index + t;
@@ -408,14 +416,21 @@ kalman_scan_cluster_kernel(const float4* __restrict__ measure, const float2* __r
     float4* nxt = s_band + (cur ^ 1) * cap;
     for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
       const int p = p_lo + i;
-      const float4 z = measure[fr + p];
+      const bool pre = i == (int)threadIdx.x;   // the prefetched pixel
+      const float4 z = pre ? z_n : measure[fr + p];
+      const float2 fl_in = pre ? fl_n : flow[fr + p];
+      const float sw_in = pre ? sw_n : sigma_w[fr + p];
+      if (pre && t + 1 < T) {
+        const int64_t q = fr + P + p;
+        z_n = measure[q]; fl_n = flow[q]; sw_n = sigma_w[q];
+      }
       float4 xm, xp;
       float n0 = 0.f, n1 = 0.f, n2 = 0.f;
       int2 tp = make_int2(0, 0);
       if (reinit) {
         xm = z; xp = z;
       } else {
-        const float2 fl = flow[fr + p];
+        const float2 fl = fl_in;
         const int y = p / GW, x = p - y * GW;
         const float cx = (float)x + fl.x, cy = (float)y + fl.y;
         const float x0 = floorf(cx), y0 = floorf(cy);
@@ -431,7 +446,7 @@ kalman_scan_cluster_kernel(const float4* __restrict__ measure, const float2* __r
         xm.y = ((w00 * i00.y + w01 * i01.y) + w10 * i10.y) + w11 * i11.y;
         xm.z = ((w00 * i00.z + w01 * i01.z) + w10 * i10.z) + w11 * i11.z;
         const float sl = ((w00 * i00.w + w01 * i01.w) + w10 * i10.w) + w11 * i11.w;
-        const float sw = sigma_w[fr + p];
+        const float sw = sw_in;
         const float last_var = fmaxf(sl * sl, minvar);
         const float trans_var = fmaxf(sw * sw, minvar);
         xm.w = sqrtf(trans_var + last_var);
@@ -488,6 +503,13 @@ int launch_kalman_scan(const float* measure, const float* flow, const float* sig
   const int num_sms = sm_count(dev0);
   // latency regime only: with many sequences one CTA per sequence already fills the SMs (measured: 148 sequences run
   // 8.2 us/frame-step single-CTA vs 25 us as 592 cluster CTAs; 8 sequences run 7.2 vs 4.8 us/frame)
+  // cluster size: the largest of 8..2 that leaves every CTA >= 2 grid rows and the clusters half of the SMs (measured on a B200, one
+  // 256-frame sequence of 60x80: 8 CTAs 2.78 us per frame, 6: 2.97, 5: 3.16, 4: 4.11 -- 1200 pixels per CTA are two passes of its
+  // 1024 threads --, 3: 4.44, single CTA 6.33; eight sequences: 3.11 / 3.33 / 3.49 / 4.97 / 5.16 / 7.35); KFN_SCAN_CLUSTER_SIZE pins it
+  static const int forced = [] { const char* e = getenv("KFN_SCAN_CLUSTER_SIZE"); const int v = e ? atoi(e) : 0;
+                                 return (v >= 2 && v <= kScanClusterMax) ? v : 0; }();
+  int kScanCluster = forced ? forced : kScanClusterMax;
+  while (!forced && kScanCluster > 2 && !(GH >= 2 * kScanCluster && 2 * S * kScanCluster <= num_sms)) --kScanCluster;
   if (use_cluster && GH >= 2 * kScanCluster && 2 * S * kScanCluster <= num_sms) {
     Xform Xc;
     for (int i = 0; i < 16; ++i) Xc.m[i] = T16_host[i];
@@ -501,11 +523,22 @@ int launch_kalman_scan(const float* measure, const float* flow, const float* sig
       KFN_CUDA_OK(cudaFuncSetAttribute(kalman_scan_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_dev[dev_c & 63] = true;
     }
-    kalman_scan_cluster_kernel<<<S * kScanCluster, 1024, smem_c, st>>>(
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(S * kScanCluster));
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = smem_c;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)kScanCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    KFN_CUDA_OK(cudaLaunchKernelEx(&cfg, kalman_scan_cluster_kernel,
         reinterpret_cast<const float4*>(measure), reinterpret_cast<const float2*>(flow), sigma_w,
         reinterpret_cast<const float4*>(state_in), reinterpret_cast<float4*>(state_out), Xc, T, GH, GW, first_index,
         reinit_period, nis_gate, reinterpret_cast<float4*>(out_map), reinterpret_cast<float4*>(temp),
-        reinterpret_cast<float4*>(kf), nis, reinterpret_cast<int2*>(taps));
+        reinterpret_cast<float4*>(kf), nis, reinterpret_cast<int2*>(taps)));
     KFN_LAUNCH_OK();
     return KFN_OK;
   }

@@ -50,7 +50,7 @@ layers = [
     conv("U-Net/conv6", R * 64, 3, 48, 16), conv("U-Net/prediction", R * 64, 3, 16, 1, out_b=4),
     conv("FC fc1", R, 1, 128, 64), conv("FC fc2", R, 1, 64, 32), conv("FC uncertainty", R, 1, 32, 1, out_b=4),
     ("softmax + flow", 0, R * (64 * 4 + 4 + 8 + 4)),
-    ("Kalman scan (16 frames, cluster of 4 CTAs)", 0, 16 * 364800),
+    ("Kalman scan (16 frames, thread-block cluster)", 0, 16 * 364800),
 ]
 rows = list(csv.DictReader(open(os.path.join(ROOT, "profiles", tag + "_launches.csv"))))[:len(layers)]
 print("| # | layer (one launch) | kernel | µs | GFLOP | TFLOP/s | % bf16 burst peak | MB | GB/s | % HBM peak |")
