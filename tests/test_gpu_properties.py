@@ -135,3 +135,44 @@ def test_edge_cases_single_frame_every_frame_reinit_and_oversized_batches(staged
     from kfnet_b200._lib import KfnError
     with pytest.raises((KfnError, AssertionError)):
         eng.eval_sequences(imgs[:0].unsqueeze(0).contiguous(), Tm)                  # empty problem -> KFN_ERR_ARG, not a launch
+
+
+_SCAN_SNIPPET = r"""
+import hashlib, sys
+import numpy as np, torch
+sys.path.insert(0, %r)
+from kfnet_b200.engine import Engine
+from kfnet_b200.train import initial_weights
+eng = Engine(initial_weights(0), mode="fp32", image_size=(480, 640))
+g = torch.Generator().manual_seed(3)
+S, T = 2, 11
+meas = torch.randn(S, T, 60, 80, 4, generator=g); meas[..., 3] = meas[..., 3].abs() + 0.05
+flow = torch.rand(S, T, 60, 80, 2, generator=g) * 9 - 5          # beyond the [-4, 3] window: clipped-neighbour taps at the borders
+sig = torch.rand(S, T, 60, 80, generator=g) * 0.2 + 0.01
+Tm = np.eye(4, dtype=np.float32); Tm[0, 3] = 0.5; Tm[1, 0] = 0.1
+r = eng.kalman_scan(meas.cuda().contiguous(), flow.cuda().contiguous(), sig.cuda().contiguous(), Tm, reinit_period=5, nis_gate=True,
+                    diagnostics=True, want_state=True)
+h = hashlib.sha256()
+for k in ("out_map", "temp", "kf", "nis", "taps", "state"):
+    h.update(r[k].cpu().numpy().tobytes())
+print("SCANHASH", h.hexdigest())
+"""
+
+
+def test_scan_cluster_sizes_bit_identical():
+    """The thread-block-cluster scan (any cluster size) is the single-CTA scan spread over several SMs: same arithmetic in the same
+    order, so every output -- maps, priors, posteriors, NIS, taps, carried state -- has identical bits.  The cluster size is read once
+    per process (KFN_SCAN_CLUSTER_SIZE / KFN_SCAN_CLUSTER), hence one subprocess per variant."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hashes = {}
+    for name, env in (("single CTA", {"KFN_SCAN_CLUSTER": "0"}), ("cluster 5", {"KFN_SCAN_CLUSTER_SIZE": "5"}), ("default cluster", {})):
+        e = dict(os.environ)
+        e.pop("KFN_SCAN_CLUSTER", None); e.pop("KFN_SCAN_CLUSTER_SIZE", None)
+        e.update(env)
+        out = subprocess.run([sys.executable, "-c", _SCAN_SNIPPET % root], env=e, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        hashes[name] = [l.split()[1] for l in out.stdout.splitlines() if l.startswith("SCANHASH")][0]
+    assert len(set(hashes.values())) == 1, hashes
