@@ -737,7 +737,16 @@ using namespace kfn;
 // ====================================================================================================================
 extern "C" {
 
+static int train_begin_impl(kfn_handle* h, int batch, int train_scoordnet, int train_oflownet);
+
+// a failed begin leaves NO training state behind (kfn_train_step on a half-built state would read unallocated buffers)
 int kfn_train_begin(kfn_handle* h, int batch, int train_scoordnet, int train_oflownet) {
+  const int rc = train_begin_impl(h, batch, train_scoordnet, train_oflownet);
+  if (rc != KFN_OK && h && h->train) { train_state_free(h->train); h->train = nullptr; }
+  return rc;
+}
+
+static int train_begin_impl(kfn_handle* h, int batch, int train_scoordnet, int train_oflownet) {
   KFN_REQUIRE(h, "null handle");
   KFN_REQUIRE(h->mode == KFN_MODE_FP32, "training runs in KFN_MODE_FP32 (the reference's arithmetic)");
   KFN_REQUIRE(batch >= 2 && batch <= 16, "training window of 2..16 frames (reference: 4)");
