@@ -93,6 +93,7 @@ struct __align__(8) TcParams {
   // tensor); the [BN x 32] weight tile is resident.  No im2col tensor ever exists in HBM.
   int im2col;
   int ph16;                     // merged deconv with four 16-channel phases: one-wait epilogue (upconv0)
+  int wres;                     // non-halo layers: every (tap, chunk) weight tile resident at the smem base, stages hold only A
   int par_issue;                // > 0: warp-parallel TMA issue, this many k-blocks (lanes) per pass (<= stages)
   const uint8_t* img;
   uint32_t tap_off16[9];        // halo: ((1+dy) * 10*bn + (1+dx)) * row_bytes / 16 per tap
@@ -152,10 +153,15 @@ struct TileIter {
 // instructions instead of a descriptor rebuild.
 template <int KSTEPS>
 __device__ __forceinline__ void mma_role(const TcParams& p, uint32_t smem_base, uint32_t tmem_base, int total_tiles, int kblocks,
-                                         uint64_t* s_full, uint64_t* s_empty, uint64_t* s_tfull, uint64_t* s_tempty) {
+                                         uint64_t* s_full, uint64_t* s_empty, uint64_t* s_tfull, uint64_t* s_tempty, uint64_t* s_wbar) {
   const uint64_t desc_fixed = ((uint64_t)p.desc_hi << 32) | (1ull << 16);
   const uint64_t stage16 = (uint64_t)(p.stage_bytes >> 4);
-  const uint64_t a0 = desc_fixed | (uint64_t)(smem_base >> 4);
+  // resident weights (TcParams::wres): tile of k-block kb at smem_base + kb * w_tile_bytes, the A stages behind them
+  const uint32_t wres = (uint32_t)p.wres;
+  if (wres) mbar_wait(smem_u32(s_wbar), 0);
+  const uint64_t a0 = desc_fixed | (uint64_t)((smem_base + (wres ? p.w_bytes_total : 0u)) >> 4);
+  const uint64_t bres0 = desc_fixed | (uint64_t)(smem_base >> 4);
+  const uint64_t wtile16 = (uint64_t)(p.w_tile_bytes >> 4);
   const uint64_t b_off = (uint64_t)(p.a_bytes >> 4);
   int s = 0, j = 0;
   uint32_t ph = 0;
@@ -170,7 +176,7 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint32_t smem_base, 
     for (int kb = 0; kb < kblocks; ++kb) {
       mbar_wait(smem_u32(&s_full[s]), ph);
       tc_fence_after();
-      umma_kblock<KSTEPS>(tmem_d, adesc, adesc + b_off, p.idesc, kb ? 1u : 0u);
+      umma_kblock<KSTEPS>(tmem_d, adesc, wres ? bres0 + (uint64_t)kb * wtile16 : adesc + b_off, p.idesc, kb ? 1u : 0u);
       umma_commit(smem_u32(&s_empty[s]));       // frees the smem stage once these MMAs retire
       adesc += stage16;
       if (++s == p.stages) { s = 0; ph ^= 1u; adesc = a0; }
@@ -584,6 +590,15 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
       // another lane of the pass leaving its wait loop.
       const int G = p.par_issue;
       const int kpt = p.ntaps * p.cpk;                    // k-blocks per tile: (tap, chunk); a fused-limb stage holds every limb
+      const uint32_t stage0 = smem_base + (p.wres ? p.w_bytes_total : 0u);
+      if (p.wres && lane < kpt) {                         // resident weights: lane l fetches the tile of k-block l (kpt <= 32 here)
+        const uint32_t wbar = smem_u32(&s_wbar);
+        if (lane == 0) mbar_expect_tx(wbar, (uint32_t)kpt * p.b_bytes);
+        __syncwarp(__activemask());
+        const int wt = lane / p.cpk, wk = lane - wt * p.cpk;
+        tma_load_3d(smem_base + (uint32_t)lane * p.w_tile_bytes, &tmB, wbar, wk * p.KC, 0, wt);
+      }
+      __syncwarp();
       int s0 = 0;
       uint32_t ph0 = 0;
       TileIter it;
@@ -604,8 +619,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
             else { cw = w0 + (dx >> 1); cpar = dy & 1; chh = h0 + (dy >> 1); coff = (dx & 1) * p.in_cs; }
             mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);
             const uint32_t full = smem_u32(&s_full[s]);
-            const uint32_t dst = smem_base + (uint32_t)s * p.stage_bytes;
-            if (p.x3_fused) {
+            const uint32_t dst = stage0 + (uint32_t)s * p.stage_bytes;
+            if (p.wres) {
+              mbar_expect_tx(full, p.a_bytes);
+              tma_load_5d(dst, &tmA, full, coff + kc * p.KC, cw, cpar, chh, n0);
+            } else if (p.x3_fused) {
               mbar_expect_tx(full, (uint32_t)p.n_limbs_a * p.a_bytes + (uint32_t)p.n_limbs_w * p.b_bytes);
               for (int la = 0; la < p.n_limbs_a; ++la)
                 tma_load_5d(dst + (uint32_t)la * p.a_bytes, &tmA, full, coff + la * p.in_ls + kc * p.KC, cw, cpar, chh, n0);
@@ -627,6 +645,13 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
       uint32_t ph = 0;
       TileIter it, pf;
       pf.init(p, total_tiles);
+      if (p.wres) {   // resident weights: every (tap, chunk) tile once, one barrier (as in halo mode)
+        const uint32_t wbar = smem_u32(&s_wbar);
+        mbar_expect_tx(wbar, (uint32_t)(p.ntaps * p.cpk) * p.b_bytes);
+        for (int tap = 0; tap < p.ntaps; ++tap)
+          for (int kc = 0; kc < p.cpk; ++kc)
+            tma_load_3d(smem_base + (uint32_t)(tap * p.cpk + kc) * p.w_tile_bytes, &tmB, wbar, kc * p.KC, 0, tap);
+      }
       // prefetch the centre-tap box of future tiles (the other taps overlap it except for a 1-pixel rim)
       auto prefetch_tile = [&](const TileIter& t) {
         if (t.nt != 0) return;
@@ -666,10 +691,10 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
             for (int kc = 0; kc < p.cpk; ++kc) {
               mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);
               const uint32_t full = smem_u32(&s_full[s]);
-              const uint32_t a_dst = smem_base + (uint32_t)s * p.stage_bytes;
-              mbar_expect_tx(full, p.a_bytes + p.b_bytes);
+              const uint32_t a_dst = smem_base + (p.wres ? p.w_bytes_total : 0u) + (uint32_t)s * p.stage_bytes;
+              mbar_expect_tx(full, p.wres ? p.a_bytes : p.a_bytes + p.b_bytes);
               tma_load_5d(a_dst, &tmA, full, a_c0 + kc * p.KC, cw, cpar, chh, n0);
-              tma_load_3d(a_dst + p.a_bytes, &tmB, full, w_c0 + kc * p.KC, nt * p.BN, tap);
+              if (!p.wres) tma_load_3d(a_dst + p.a_bytes, &tmB, full, w_c0 + kc * p.KC, nt * p.BN, tap);
               if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
           }
@@ -695,9 +720,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& tmA, const CUten
         else if (ksteps == 2) mma_role_halo<2>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
         else mma_role_halo<1>(p, smem_base, tmem_base, total_tiles, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
       } else {
-        if (ksteps == 4) mma_role<4>(p, smem_base, tmem_base, total_tiles, kblocks, s_full, s_empty, s_tfull, s_tempty);
-        else if (ksteps == 2) mma_role<2>(p, smem_base, tmem_base, total_tiles, kblocks, s_full, s_empty, s_tfull, s_tempty);
-        else mma_role<1>(p, smem_base, tmem_base, total_tiles, kblocks, s_full, s_empty, s_tfull, s_tempty);
+        if (ksteps == 4) mma_role<4>(p, smem_base, tmem_base, total_tiles, kblocks, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
+        else if (ksteps == 2) mma_role<2>(p, smem_base, tmem_base, total_tiles, kblocks, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
+        else mma_role<1>(p, smem_base, tmem_base, total_tiles, kblocks, s_full, s_empty, s_tfull, s_tempty, &s_wbar);
       }
     }
   } else {
@@ -1588,6 +1613,15 @@ int prepare_conv_tc(const ConvGeom& g, const void* in, const void* w_packed, int
       p.stage_bytes = p.a_bytes;
       p.w_tile_bytes = w_tile_bytes; p.w_bytes_total = resident = w_tile_bytes;
       plan->threads += 96;
+    }
+    // resident weights for the small non-halo layers (plain bf16, one N tile): a third to a fifth of a tile's TMA lines are weight rows
+    // that every tile re-fetches; with at most a third of the pipeline budget they stay at the smem base for the kernel's lifetime
+    static const bool wres_on = env_flag("KFN_TC_WRES", true);
+    if (wres_on && !g.im2col_u8 && !g.diff_cur && !p.pair && !x3 && !g.half_limbs && p.n_terms == 1 && p.n_tiles == 1 &&
+        g.ntaps * p.cpk <= 32 && 3u * w_total <= budget) {
+      p.wres = 1;
+      p.stage_bytes = (p.a_bytes + 1023u) & ~1023u;
+      p.w_tile_bytes = w_tile_bytes; p.w_bytes_total = resident = w_total;
     }
     int stages = (int)((budget - resident) / p.stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
