@@ -105,15 +105,55 @@ class Trainer:
         return path
 
 
+def window_stream(image_paths, label_paths, groups, Tinv, spec, n, shuffle=False, seed=None, prefetch=3, workers=2):
+    """The training input queue of train.py:195-239 as a generator of `n` windows `(group, images u8 [B,H,W,3], gt8, mask8)`.
+
+    Order = `tf.train.string_input_producer(indexes, shuffle=FLAGS.shuffle)` (train.py:205): the window list is walked epoch after
+    epoch, in list order with `shuffle=False` (the reference's default, train.py:17) and in a fresh random permutation per epoch with
+    `shuffle=True` (`seed` pins the permutations; TF draws them from the graph seed).  The reference decodes with ONE queue-runner
+    thread and a capacity of 4 batches (train.py:234-239); here PNG decode, the raw-float label reads and `prepare_window` of the next
+    `prefetch` windows run on a small thread pool while the GPU executes the current step, and results are delivered in queue order."""
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+    from .eval import load_image, load_label
+
+    def order():
+        rng = np.random.default_rng(seed)
+        while True:
+            idx = rng.permutation(len(groups)) if shuffle else range(len(groups))
+            for gi in idx:
+                yield groups[int(gi)]
+
+    def load(g):
+        images = np.stack([load_image(image_paths[f]) for f in g])
+        labels = np.stack([load_label(label_paths[f], spec.image_size) for f in g])
+        gt8, mask8 = prepare_window(labels, Tinv)
+        return g, images, gt8, mask8
+
+    if n <= 0 or not groups:
+        return
+    src = order()
+    with ThreadPoolExecutor(max_workers=max(1, int(workers))) as pool:
+        pending = deque()
+        issued = 0
+        while issued < n and len(pending) < max(1, int(prefetch)):
+            pending.append(pool.submit(load, next(src))); issued += 1
+        while pending:
+            item = pending.popleft().result()
+            if issued < n:
+                pending.append(pool.submit(load, next(src))); issued += 1
+            yield item
+
+
 def train(image_list, label_list, transform_file, snapshot=None, scene="stairs", model_folder="", max_steps=None, fix_flownet=False,
           weights=None, display=DISPLAY, snapshot_every=SNAPSHOT, device=None, quiet=False, step=0, reset_step=-1, scoordnet="",
-          oflownet=""):
-    """The loop of train.py:347-420 over the scene's training windows, in order (the reference shuffles its queue with a
-    fixed seed; order only matters for reproducing a particular run).  `step` / `reset_step` set global_step (train.py:361-362);
+          oflownet="", shuffle=False, seed=None):
+    """The loop of train.py:347-420 over the scene's training windows, fed by `window_stream` (list order like the reference's
+    default `--shuffle=False`, or a fresh permutation per epoch).  `step` / `reset_step` set global_step (train.py:361-362);
     `scoordnet` / `oflownet` = model folders whose newest snapshot overrides the 'ScoreNet' / 'Temporal' scope (train.py:402-407);
     with both given the step is reset to 4 x stepvalue like set_stepvalue does (train.py:346-348); the loop ends at
     max_steps = 5 x stepvalue (train.py:349) unless `max_steps` says otherwise."""
-    from .eval import get_transform, load_image, load_label, load_snapshot_weights, read_lines
+    from .eval import get_transform, load_snapshot_weights, read_lines
     image_paths, label_paths = read_lines(image_list), read_lines(label_list)
     assert len(image_paths) == len(label_paths)
     spec = KFNetDataSpec(scene=scene)
@@ -135,11 +175,7 @@ def train(image_list, label_list, transform_file, snapshot=None, scene="stairs",
     tr = Trainer(w, spec, fix_flownet=fix_flownet, device=device, step=step, stepvalue=stepvalue)
     n = max_steps if max_steps is not None else max(0, stepvalue * 5 - step + 1)           # while step <= FLAGS.max_steps
     hist = []
-    for it in range(n):
-        g = groups[it % len(groups)]
-        images = np.stack([load_image(image_paths[f]) for f in g])
-        labels = np.stack([load_label(label_paths[f], spec.image_size) for f in g])
-        gt8, mask8 = prepare_window(labels, Tinv)
+    for it, (_, images, gt8, mask8) in enumerate(window_stream(image_paths, label_paths, groups, Tinv, spec, n, shuffle=shuffle, seed=seed)):
         out = tr.step(images, gt8, mask8)
         hist.append(out)
         if not quiet and (it % display == 0):
@@ -162,12 +198,14 @@ def main(argv=None):
     ap.add_argument("--scoordnet", default="", help="model folder whose ScoreNet variables are restored over the snapshot")
     ap.add_argument("--oflownet", default="", help="model folder whose Temporal variables are restored over the snapshot")
     ap.add_argument("--gpu", type=int, default=0)
+    ap.add_argument("--shuffle", action="store_true", help="FLAGS.shuffle of train.py:17: a fresh permutation of the windows per epoch")
     a = ap.parse_args(argv)
     from .eval import get_snapshot
     snapshot, step = get_snapshot(a.model_folder)
     train(os.path.join(a.input_folder, "image_list.txt"), os.path.join(a.input_folder, "label_list.txt"),
           os.path.join(a.input_folder, "transform.txt"), snapshot, scene=a.scene, model_folder=a.model_folder, max_steps=a.max_steps,
-          fix_flownet=a.fix_flownet, device=a.gpu, step=step, reset_step=a.reset_step, scoordnet=a.scoordnet, oflownet=a.oflownet)
+          fix_flownet=a.fix_flownet, device=a.gpu, step=step, reset_step=a.reset_step, scoordnet=a.scoordnet, oflownet=a.oflownet,
+          shuffle=a.shuffle)
 
 
 if __name__ == "__main__":
